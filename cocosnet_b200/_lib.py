@@ -1,0 +1,59 @@
+"""ctypes binding of libcocos_b200.so (include/cocos_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or an
+entry point is absent, importing/using the ops raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcocos_b200.so")
+
+_c_int, _c_float, _c_ll, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_void_p
+
+# name -> argtypes (restype is int unless noted); mirrors include/cocos_b200.h
+SIGNATURES = {
+    "cocos_abi_version": [],
+    "cocos_last_error": [],
+    "cocos_pack_rows_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
+    "cocos_pack_v_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
+    "cocos_corr_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                            _c_float, _vp],
+    "cocos_gemm_f16": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
+                       _c_float, _c_int, _vp],
+}
+
+_lib = None
+
+
+class CocosError(RuntimeError):
+    pass
+
+
+def build():
+    """Compile the extension in-tree (nvcc, sm_100a)."""
+    import subprocess
+    subprocess.check_call(["bash", os.path.join(_HERE, "csrc", "build.sh")])
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CocosError(
+            "libcocos_b200.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or cocosnet_b200/csrc/build.sh. There is no CPU/PyTorch fallback for the hot path." % LIB_PATH)
+    h = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_char_p if name == "cocos_last_error" else ctypes.c_int
+    _lib = h
+    return h
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cocos_last_error()
+        raise CocosError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))

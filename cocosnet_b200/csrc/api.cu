@@ -1,0 +1,43 @@
+// extern "C" boundary of libcocos_b200.so — see include/cocos_b200.h.
+#include "../../include/cocos_b200.h"
+
+#include "corr_kernels.h"
+#include "tmap.h"
+
+using namespace cocos;
+
+extern "C" {
+
+int cocos_abi_version(void) { return COCOS_ABI_VERSION; }
+const char* cocos_last_error(void) { return get_error(); }
+
+int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, void* stream) {
+  return pack_rows_f16_launch(src, dst, B, C, N, Kp, split_mode, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, void* stream) {
+  return pack_v_f16_launch(src, dst, B, Cv, Nk, Cvp, Nkp, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
+                        int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, void* stream) {
+  if (!q || !k || !vt || !out) {
+    set_error("cocos_corr_warp_fwd: null pointer argument");
+    return -1;
+  }
+  return corr_warp_fwd_launch(q, k, vt, out, lse, corr, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb, int ldc,
+                   long long stride_a, long long stride_b, long long stride_c, float alpha, int accumulate,
+                   void* stream) {
+  if (!a || !b || !c) {
+    set_error("cocos_gemm_f16: null pointer argument");
+    return -1;
+  }
+  return gemm_f16_launch(a, b, c, batch, M, N, K, lda, ldb, ldc, stride_a, stride_b, stride_c, alpha, accumulate,
+                         static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// Internal launch prototypes shared between the kernel translation units and
+// the C-ABI (api.cu).  All pointers are device pointers; every launcher
+// returns 0 or a negative error code after cocos::set_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cocos {
+
+int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
+                         int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
+
+// C[b] (MxN fp32, row-major, ldc) = alpha * A[b] (MxK fp16, K contiguous) * B[b]^T (NxK fp16) (+ C if accumulate)
+int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb,
+                    int ldc, long long stride_a, long long stride_b, long long stride_c, float alpha,
+                    int accumulate, cudaStream_t stream);
+
+int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
+                         cudaStream_t stream);
+int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, cudaStream_t stream);
+
+}  // namespace cocos

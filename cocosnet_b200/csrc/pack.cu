@@ -1,0 +1,99 @@
+// HBM-bound layout/precision prologue kernels for K1.
+//   pack_rows_f16 : fp32 [B, C, N] (channel-major, the reference's
+//                   theta/phi layout, correspondence.py:274-289) ->
+//                   fp16 [B, N, Kt] (position-major, K contiguous) that TMA
+//                   stages as the K-major MMA operand; optional 2-term fp16
+//                   split laid out along K so ONE GEMM accumulates
+//                   hi*hi + lo*hi + hi*lo.
+//   pack_v_f16    : fp32 [B, Cv, Nk] -> fp16 [B, Cvp, Nkp], zero padded.
+#include "corr_kernels.h"
+#include "tmap.h"
+
+#include <cuda_fp16.h>
+
+namespace cocos {
+
+namespace {
+
+constexpr int TC = 64;  // channels per tile
+constexpr int TN = 32;  // positions per tile
+
+// split_mode 0: [h]; 1: [h, l, h] (query side); 2: [h, h, l] (key side)
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int N, int Kp, int split_mode) {
+  __shared__ float tile[TC][TN + 1];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * TC;
+  const int n0 = blockIdx.x * TN;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* s = src + static_cast<size_t>(b) * C * N;
+#pragma unroll
+  for (int i = 0; i < TC; i += 8) {
+    const int c = c0 + ty + i, n = n0 + tx;
+    tile[ty + i][tx] = (c < C && n < N) ? s[static_cast<size_t>(c) * N + n] : 0.f;
+  }
+  __syncthreads();
+  const int nseg = split_mode ? 3 : 1;
+  const int Kt = Kp * nseg;
+  __half* d = dst + static_cast<size_t>(b) * N * Kt;
+  // each thread writes 2 adjacent channels (half2) for 4 positions
+  const int cx = (threadIdx.x & 31) * 2;  // 0..62
+  const int nrow = threadIdx.x >> 5;      // 0..7
+#pragma unroll
+  for (int i = 0; i < TN; i += 8) {
+    const int n = n0 + nrow + i;
+    const int c = c0 + cx;
+    if (n < N && c < Kp) {
+      const float x0 = tile[cx][nrow + i], x1 = tile[cx + 1][nrow + i];
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half2 hi = __halves2half2(h0, h1);
+      __half* row = d + static_cast<size_t>(n) * Kt + c;
+      if (!split_mode) {
+        *reinterpret_cast<__half2*>(row) = hi;
+      } else {
+        const __half2 lo = __halves2half2(__float2half_rn(x0 - __half2float(h0)),
+                                          __float2half_rn(x1 - __half2float(h1)));
+        *reinterpret_cast<__half2*>(row) = hi;
+        *reinterpret_cast<__half2*>(row + Kp) = (split_mode == 1) ? lo : hi;
+        *reinterpret_cast<__half2*>(row + 2 * Kp) = (split_mode == 1) ? hi : lo;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_v_kernel(const float* __restrict__ src, __half* __restrict__ dst, int Cv, int Nk, int Cvp, int Nkp) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Nkp) return;
+  float v = 0.f;
+  if (c < Cv && n < Nk) v = src[(static_cast<size_t>(b) * Cv + c) * Nk + n];
+  dst[(static_cast<size_t>(b) * Cvp + c) * Nkp + n] = __float2half_rn(v);
+}
+
+}  // namespace
+
+int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
+                         cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || N <= 0 || Kp < C || (Kp % 2) != 0 || split_mode < 0 || split_mode > 2) {
+    set_error("pack_rows_f16: bad arguments (B=%d C=%d N=%d Kp=%d split=%d)", B, C, N, Kp, split_mode);
+    return -1;
+  }
+  dim3 grid((N + TN - 1) / TN, (Kp + TC - 1) / TC, B);
+  pack_rows_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), C, N, Kp, split_mode);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, cudaStream_t stream) {
+  if (B <= 0 || Cv <= 0 || Nk <= 0 || Cvp < Cv || Nkp < Nk) {
+    set_error("pack_v_f16: bad arguments (B=%d Cv=%d Nk=%d Cvp=%d Nkp=%d)", B, Cv, Nk, Cvp, Nkp);
+    return -1;
+  }
+  dim3 grid((Nkp + 255) / 256, Cvp, B);
+  pack_v_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), Cv, Nk, Cvp, Nkp);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cocos

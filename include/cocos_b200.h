@@ -1,0 +1,68 @@
+/* cocos_b200 — C-ABI of the B200-native CoCosNet hot path (libcocos_b200.so).
+ *
+ * The reference (microsoft/CoCosNet) has no native boundary: its hot path is
+ * Python calling ATen.  This header is the boundary we put underneath the
+ * reference's module API; each entry point cites the reference
+ * expression it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch); the
+ *     library never allocates or frees device memory and never synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, negative on error; cocos_last_error() gives the
+ *     message (thread local).  Nothing throws across the boundary;
+ *   - fp16 operand buffers are produced by the cocos_pack_* entry points.
+ */
+#ifndef COCOS_B200_H
+#define COCOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COCOS_ABI_VERSION 1
+
+int cocos_abi_version(void);
+const char* cocos_last_error(void);
+
+/* fp32 [B, C, N] (channel-major, the layout of theta/phi after
+ * correspondence.py:274/276 view/unfold and :277-280 normalisation) ->
+ * fp16 [B, N, Kt], Kt = Kp * (split_mode ? 3 : 1), Kp >= C zero padded, Kp%2==0.
+ * This is the `theta.permute(0, 2, 1)` of correspondence.py:281 plus the
+ * operand rounding.  split_mode: 0 = plain fp16; 1 = query side [hi, lo, hi];
+ * 2 = key side [hi, hi, lo] (one GEMM then sums hi*hi + lo*hi + hi*lo). */
+int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, void* stream);
+
+/* fp32 [B, Cv, Nk] (channel-major exemplar values: avg-pooled ref image
+ * correspondence.py:313-315, unfolded patches :311, ref_seg :330-332) ->
+ * fp16 [B, Cvp, Nkp], zero padded; Cvp % 16 == 0, Nkp % 8 == 0. */
+int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, void* stream);
+
+/* K1, fused correlation + softmax + warp.  Replaces
+ *   f = matmul(theta_permute, phi)          correspondence.py:291
+ *   f_WTA = f / temperature                 correspondence.py:304
+ *   f_div_C = softmax(f_WTA, -1)            correspondence.py:307
+ *   y = matmul(f_div_C, ref)                correspondence.py:318 (and :334, :343-344,
+ *                                           :362, :368, :370 with operands swapped)
+ * q  : fp16 [B, Nq, Kd]   k : fp16 [B, Nk, Kd]   (Kd % 64 == 0)
+ * vt : fp16 [B, Cvp, Nkp] (values, channel-major)
+ * out: fp32 [B, Cv, Nq]   = y.permute(0, 2, 1)  (correspondence.py:323)
+ * lse: fp32 [B, Nq] natural-log row log-sum-exp of scale*f (may be NULL)
+ * corr: fp32 [B, Nq, Nk] scaled logits f/temperature (may be NULL; the
+ *       `return_corr=True` output of correspondence.py:305-306)
+ * scale = 1 / temperature. */
+int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
+                        int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, void* stream);
+
+/* Batched tcgen05 GEMM: C[b] (MxN fp32 row-major, ldc) = alpha * A[b] (MxK fp16,
+ * K contiguous, lda) * B[b]^T (NxK fp16, ldb) (+ C[b] if accumulate).  Strides in
+ * elements.  The torch.matmul / 1x1-conv call sites of correspondence.py:291
+ * (return_corr), architecture.py:116-125 and the K1 backward. */
+int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb, int ldc,
+                   long long stride_a, long long stride_b, long long stride_c, float alpha, int accumulate,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COCOS_B200_H */

@@ -1,0 +1,168 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called
+through the C-ABI, against the numpy oracle and the committed goldens."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def test_pack_rows_and_v_exact():
+    from cocosnet_b200 import ops
+    x = torch.randn(2, 70, 100, device="cuda")
+    y = ops.pack_rows(x)
+    assert y.shape == (2, 100, 128)
+    assert torch.equal(y[:, :, :70], x.permute(0, 2, 1).half())
+    assert float(y[:, :, 70:].abs().max()) == 0.0
+    y3 = ops.pack_rows(x, split=2)
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    assert torch.equal(y3[:, :, 128:198], hi.permute(0, 2, 1))
+    assert torch.equal(y3[:, :, 256:326], lo.permute(0, 2, 1))
+    v = torch.randn(2, 3, 100, device="cuda")
+    pv = ops.pack_v(v)
+    assert pv.shape == (2, 16, 104)
+    assert torch.equal(pv[:, :3, :100], v.half())
+    assert float(pv[:, 3:].abs().max()) == 0.0 and float(pv[:, :, 100:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("b,m,n,k", [(1, 128, 128, 64), (2, 256, 384, 512), (1, 200, 72, 96), (3, 130, 260, 200)])
+def test_gemm_f16(b, m, n, k):
+    from cocosnet_b200 import ops
+    a = (torch.randn(b, m, k, device="cuda") / k ** 0.5).half()
+    bb = torch.randn(b, n, k, device="cuda").half()
+    c = ops.gemm_f16(a, bb, alpha=0.5)
+    ref = 0.5 * (a.double() @ bb.double().transpose(1, 2))
+    assert _rel(c.cpu().numpy(), ref.cpu().numpy()) < 1e-5  # fp32 accumulate of exact fp16 products
+    c2 = ops.gemm_f16(a, bb, alpha=1.0, out=c.clone(), accumulate=True)
+    assert _rel(c2.cpu().numpy(), 3 * ref.cpu().numpy()) < 1e-5
+
+
+def _make_qkv(b, nq, nk, kd, cv, peaky=False, seed=0):
+    rng = np.random.default_rng(seed + nq + 3 * nk + kd)
+    q = rng.standard_normal((b, kd, nq))
+    k = rng.standard_normal((b, kd, nk))
+    if peaky and nq == nk:
+        perm = rng.permutation(nk)
+        k = q[:, :, perm] + 0.05 * rng.standard_normal((b, kd, nk))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k /= np.linalg.norm(k, axis=1, keepdims=True)
+    v = rng.uniform(-1, 1, (b, cv, nk))
+    return q.astype(np.float32), k.astype(np.float32), v.astype(np.float32)
+
+
+FWD_CASES = [
+    # b, nq, nk, kd, cv, scale, peaky
+    (1, 128, 128, 64, 3, 1.0, False),
+    (1, 128, 128, 64, 3, 100.0, False),
+    (2, 200, 300, 64, 5, 100.0, False),     # ragged rows and keys
+    (1, 576, 576, 256, 3, 100.0, True),     # near one-hot rows, online-softmax rescale
+    (1, 512, 512, 320, 20, 100.0, False),   # Kd > 256: streamed-Q path
+    (1, 256, 256, 64, 154, 100.0, False),   # wide V ([rgb | 151-class mask])
+    (1, 1024, 256, 64, 128, 1.0, False),    # SAGAN attention shape class
+]
+
+
+@pytest.mark.parametrize("b,nq,nk,kd,cv,scale,peaky", FWD_CASES)
+def test_corr_warp_fwd_vs_oracle(b, nq, nk, kd, cv, scale, peaky):
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    q, k, v = _make_qkv(b, nq, nk, kd, cv, peaky)
+    q16 = ops.pack_rows(torch.from_numpy(q).cuda())
+    k16 = ops.pack_rows(torch.from_numpy(k).cuda())
+    vt = ops.pack_v(torch.from_numpy(v).cuda())
+    out, lse, corr = ops.corr_warp_fwd(q16, k16, vt, cv, nk, scale, want_lse=True, want_corr=True)
+    # (1) kernel exactness: oracle fed the same fp16-rounded operands
+    qr = q16.float().cpu().numpy()[:, :, :kd]
+    kr = k16.float().cpu().numpy()[:, :, :kd]
+    vr = vt.float().cpu().numpy()[:, :cv, :nk].transpose(0, 2, 1)
+    o_ref, lse_ref = oc.attend(qr, kr, vr, scale)
+    assert _rel(out.cpu().numpy(), o_ref.transpose(0, 2, 1)) < 5e-4   # P is rounded to fp16 (2^-11)
+    assert np.abs(lse.cpu().numpy() - lse_ref).max() < 2e-3
+    z = (qr.astype(np.float64) @ kr.astype(np.float64).transpose(0, 2, 1)) * scale
+    assert np.abs(corr.cpu().numpy() - z).max() < 1e-4 * max(scale, 1.0)
+    # (2) north-star tolerance: 1e-3 relative vs the fp64 oracle on the fp32 inputs
+    o_true, _ = oc.attend(q.transpose(0, 2, 1), k.transpose(0, 2, 1), v.transpose(0, 2, 1), scale)
+    tol = 1e-3 if not peaky else 2e-3
+    assert _rel(out.cpu().numpy(), o_true.transpose(0, 2, 1)) < tol
+
+
+def test_corr_warp_fwd_split_precision():
+    """3-term fp16 split along K: ~1e-5 class error (strict mode)."""
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    q, k, v = _make_qkv(1, 512, 512, 256, 3, peaky=True)
+    q16 = ops.pack_rows(torch.from_numpy(q).cuda(), split=1)
+    k16 = ops.pack_rows(torch.from_numpy(k).cuda(), split=2)
+    vt = ops.pack_v(torch.from_numpy(v).cuda())
+    out, _, _ = ops.corr_warp_fwd(q16, k16, vt, 3, 512, 100.0)
+    o_true, _ = oc.attend(q.transpose(0, 2, 1), k.transpose(0, 2, 1), v.transpose(0, 2, 1), 100.0)
+    assert _rel(out.cpu().numpy(), o_true.transpose(0, 2, 1)) < 5e-4
+
+
+def test_properties_full_size():
+    """BASELINE size (N=4096, K=256): size-independent properties."""
+    from cocosnet_b200 import ops
+    b, n, kd = 2, 4096, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(b, kd, n, device="cuda", generator=g)
+    q = q / q.norm(dim=1, keepdim=True)
+    k = torch.randn(b, kd, n, device="cuda", generator=g)
+    k = k / k.norm(dim=1, keepdim=True)
+    q16, k16 = ops.pack_rows(q), ops.pack_rows(k)
+    # rows of a softmax sum to one: warping a constant image returns it
+    ones = torch.ones(b, 3, n, device="cuda")
+    out, lse, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(ones), 3, n, 100.0)
+    assert float((out - 1).abs().max()) < 2e-3
+    # linearity in V
+    v1 = torch.rand(b, 3, n, device="cuda", generator=g)
+    v2 = torch.rand(b, 3, n, device="cuda", generator=g)
+    o1, _, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(v1), 3, n, 100.0)
+    o2, _, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(v2), 3, n, 100.0)
+    o12, _, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(v1 + v2), 3, n, 100.0)
+    assert float((o1 + o2 - o12).abs().max()) < 4e-3
+    # identical keys == queries: the diagonal dominates, warp ~ identity on V
+    oid, _, _ = ops.corr_warp_fwd(q16, q16, ops.pack_v(v1), 3, n, 100.0)
+    full = torch.softmax((q16.float() @ q16.float().transpose(1, 2)) * 100.0, -1) @ v1.half().float().transpose(1, 2)
+    assert float((oid - full.transpose(1, 2)).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("name", ["ade20k_mk1", "ade20k_mk3", "ade20k_mk1_peaky", "celebahq_bilinear_cycle",
+                                  "deepfashion_patch", "small_n576_mk3"])
+def test_tail_vs_reference_golden(name):
+    """Goldens minted from the reference's own tail code (make_golden.py)."""
+    from cocosnet_b200 import corr
+    from tests.golden import cases
+    import torch.nn.functional as F
+    spec = cases.TAIL_CASES[name]
+    gold = np.load(os.path.join(GOLD, "tail_%s.npz" % name))
+    inp = {k: torch.from_numpy(v).cuda() for k, v in cases.tail_inputs(name).items()}
+    fl = dict(spec["flags"])
+    bilinear = fl.pop("warp_bilinear", False)
+    with torch.no_grad():
+        y, ex = corr.correspondence_tail(inp["theta"], inp["phi"], inp["ref_img"], ref_seg_map=inp["ref_seg"],
+                                         seg_map=inp["seg"], real_img=inp["real_img"], **fl)
+        if not fl.get("warp_patch"):
+            y = F.interpolate(y, scale_factor=4, mode="bilinear") if bilinear else F.interpolate(y, scale_factor=4)
+    tol = 2e-3 if "peaky" in name else 1e-3
+    assert _rel(y.cpu().numpy(), gold["warp_out"].astype(np.float64)) < tol
+    for k in ("warp_cycle", "warp_i2r", "warp_i2r2i"):
+        if k in gold.files:
+            assert _rel(ex[k].cpu().numpy(), gold[k].astype(np.float64)) < 2e-3, k
+    if "warp_mask" in gold.files:
+        wm = ex["warp_mask"].cpu().numpy()
+        assert _rel(wm[:, ::19], gold["warp_mask"].astype(np.float64)) < 2e-3
+        assert np.abs(wm.sum(1) - gold["warp_mask_chsum"]).max() < 2e-3
+    if "corr" in gold.files:
+        c, _ = corr.correspondence_tail(inp["theta"], inp["phi"], inp["ref_img"], return_corr=True,
+                                        match_kernel=fl["match_kernel"], pono_c=fl["pono_c"])
+        assert np.abs(c.cpu().numpy() - gold["corr"]).max() < 0.05  # fp16 operands, logits in [-100,100]
