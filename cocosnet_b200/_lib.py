@@ -19,6 +19,7 @@ SIGNATURES = {
     "cocos_pack_v_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
     "cocos_corr_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                             _c_float, _vp],
+    "cocos_corr_warp_bwd_ds": [_vp] * 10 + [_c_int] * 8 + [_c_float, _c_float, _vp],
     "cocos_gemm_f16": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
                        _c_float, _c_int, _vp],
 }

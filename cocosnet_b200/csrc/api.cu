@@ -40,4 +40,15 @@ int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int
                          static_cast<cudaStream_t>(stream));
 }
 
+int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+                           const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
+                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, void* stream) {
+  if (!q || !k || !do16 || !v16 || !d_out || !out || !lse || !ds || !dst) {
+    set_error("cocos_corr_warp_bwd_ds: null pointer argument");
+    return -1;
+  }
+  return corr_bwd_ds_launch(q, k, do16, v16, d_out, out, lse, ds, dst, pt, B, Nq, Nk, Kd, Cv, Cvk, Nkp, Nqp, scale,
+                            dscale, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -15,6 +15,10 @@ int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, in
                     int ldc, long long stride_a, long long stride_b, long long stride_c, float alpha,
                     int accumulate, cudaStream_t stream);
 
+int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+                       const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
+                       int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, cudaStream_t stream);
+
 int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
                          cudaStream_t stream);
 int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, cudaStream_t stream);

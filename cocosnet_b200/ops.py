@@ -66,10 +66,17 @@ def corr_warp_fwd(q16, k16, vt16, cv, nk, scale, want_lse=True, want_corr=False)
     return out, lse, corr
 
 
+def _req_rows(t, name):
+    """fp16 CUDA tensor [b, R, C] with unit inner stride (row pitch / batch stride free)."""
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float16 and t.dim() == 3 and t.stride(2) == 1):
+        raise _lib.CocosError("%s must be a CUDA fp16 [b,R,C] tensor with contiguous rows" % name)
+
+
 def gemm_f16(a16, b16, alpha=1.0, out=None, accumulate=False):
-    """C[b] = alpha * A[b] @ B[b]^T.  a16 [b,M,K], b16 [b,N,K] fp16 -> fp32 [b,M,N]."""
-    _req(a16, torch.float16, "a16")
-    _req(b16, torch.float16, "b16")
+    """C[b] = alpha * A[b] @ B[b]^T.  a16 [b,M,K], b16 [b,N,K] fp16 (rows may be
+    pitched views) -> fp32 [b,M,N]."""
+    _req_rows(a16, "a16")
+    _req_rows(b16, "b16")
     bt, m, k = a16.shape
     n = b16.shape[1]
     if b16.shape[0] != bt or b16.shape[2] != k:
@@ -78,7 +85,35 @@ def gemm_f16(a16, b16, alpha=1.0, out=None, accumulate=False):
         out = torch.empty((bt, m, n), dtype=torch.float32, device=a16.device)
     else:
         _req(out, torch.float32, "out")
-    _lib.check(_lib.lib().cocos_gemm_f16(a16.data_ptr(), b16.data_ptr(), out.data_ptr(), bt, m, n, k, k, k, n,
-                                         m * k, n * k, m * n, float(alpha), int(bool(accumulate)), _stream()),
-               "cocos_gemm_f16")
+    _lib.check(_lib.lib().cocos_gemm_f16(a16.data_ptr(), b16.data_ptr(), out.data_ptr(), bt, m, n, k,
+                                         a16.stride(1), b16.stride(1), n, a16.stride(0), b16.stride(0), m * n,
+                                         float(alpha), int(bool(accumulate)), _stream()), "cocos_gemm_f16")
     return out
+
+
+def cast_rows_f16(x):
+    """fp32 [B,R,C] -> fp16 [B,R,C] view of a buffer whose row pitch is a multiple of 8."""
+    _req(x, torch.float32, "x")
+    b, r, c = x.shape
+    cp = round_up(c, 8)
+    buf = torch.empty((b, r, cp), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().cocos_pack_v_f16(x.data_ptr(), buf.data_ptr(), b, r, c, r, cp, _stream()),
+               "cocos_pack_v_f16")
+    return buf[:, :, :c]
+
+
+def corr_warp_bwd_ds(q16, k16, do16, v16, d_out, out, lse, cv, scale, dscale, want_pt):
+    """K1 backward stage A -> (ds [B,Nq,Nk], dst [B,Nk,Nq], pt | None) fp16 (pitched views)."""
+    b, nq, kd = q16.shape
+    nk = k16.shape[1]
+    cvk = do16.shape[2]
+    nkp, nqp = round_up(nk, 8), round_up(nq, 8)
+    dev = q16.device
+    ds = torch.empty((b, nq, nkp), dtype=torch.float16, device=dev)
+    dst = torch.empty((b, nk, nqp), dtype=torch.float16, device=dev)
+    pt = torch.empty((b, nk, nqp), dtype=torch.float16, device=dev) if want_pt else None
+    _lib.check(_lib.lib().cocos_corr_warp_bwd_ds(q16.data_ptr(), k16.data_ptr(), do16.data_ptr(), v16.data_ptr(),
+                                                 d_out.data_ptr(), out.data_ptr(), lse.data_ptr(), ds.data_ptr(),
+                                                 dst.data_ptr(), _ptr(pt), b, nq, nk, kd, cv, cvk, nkp, nqp,
+                                                 float(scale), float(dscale), _stream()), "cocos_corr_warp_bwd_ds")
+    return ds[:, :, :nk], dst[:, :, :nq], (pt[:, :, :nq] if want_pt else None)

@@ -62,6 +62,19 @@ int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int
                    long long stride_a, long long stride_b, long long stride_c, float alpha, int accumulate,
                    void* stream);
 
+/* K1 backward, stage A (what autograd does through correspondence.py:291-318):
+ * recomputes S = q k^T and dP = dO V^T tile by tile and writes
+ *   ds  fp16 [B, Nq, Nkp] = dscale * P * (dP - D) * scale,  D[i] = sum_c dO[c,i] O[c,i]
+ *   dst fp16 [B, Nk, Nqp] = ds^T,   pt fp16 [B, Nk, Nqp] = P^T (optional, may be NULL)
+ * q,k as in cocos_corr_warp_fwd; do16 fp16 [B,Nq,Cvk] / v16 fp16 [B,Nk,Cvk] are dO / V
+ * position-major (cocos_pack_rows_f16, Cvk % 64 == 0); d_out,out fp32 [B,Cv,Nq]; lse
+ * from the forward.  The input gradients then follow from three cocos_gemm_f16 calls:
+ *   dq^T[Kd,Nq] = k_cm[Kd,Nk] x ds,  dk^T[Kd,Nk] = q_cm[Kd,Nq] x dst,  dv^T[Cv,Nk] = do_cm[Cv,Nq] x pt,
+ * each with alpha = 1/dscale (dv: alpha = 1). */
+int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+                           const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
+                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

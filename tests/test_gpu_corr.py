@@ -166,3 +166,32 @@ def test_tail_vs_reference_golden(name):
         c, _ = corr.correspondence_tail(inp["theta"], inp["phi"], inp["ref_img"], return_corr=True,
                                         match_kernel=fl["match_kernel"], pono_c=fl["pono_c"])
         assert np.abs(c.cpu().numpy() - gold["corr"]).max() < 0.05  # fp16 operands, logits in [-100,100]
+
+
+BWD_CASES = [
+    # b, nq, nk, kd, cv, scale
+    (1, 128, 128, 64, 3, 100.0),
+    (2, 200, 300, 128, 5, 100.0),
+    (1, 384, 256, 256, 154, 100.0),
+    (1, 256, 256, 64, 48, 1.0),
+]
+
+
+@pytest.mark.parametrize("b,nq,nk,kd,cv,scale", BWD_CASES)
+def test_attend_backward_vs_oracle(b, nq, nk, kd, cv, scale):
+    """Gradients of the fused primitive vs the fp64 oracle (analytic backward,
+    itself checked against torch autograd on CPU in test_oracle_golden.py)."""
+    from cocosnet_b200 import corr
+    from oracle import corr_oracle as oc
+    q, k, v = _make_qkv(b, nq, nk, kd, cv)
+    rng = np.random.default_rng(11)
+    d_o = (rng.standard_normal((b, cv, nq)) * 1e-3).astype(np.float32)
+    tq, tk, tv = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (q, k, v))
+    out = corr.attend(tq, tk, tv, scale)
+    out.backward(torch.from_numpy(d_o).cuda())
+    dq, dk, dv = oc.attend_backward(q.transpose(0, 2, 1), k.transpose(0, 2, 1), v.transpose(0, 2, 1), scale,
+                                    d_o.transpose(0, 2, 1))
+    # gradients carry the fp16 rounding of operands, P, dS (2^-11 each) amplified by scale
+    assert _rel(tq.grad.cpu().numpy(), dq.transpose(0, 2, 1)) < 1e-2
+    assert _rel(tk.grad.cpu().numpy(), dk.transpose(0, 2, 1)) < 1e-2
+    assert _rel(tv.grad.cpu().numpy(), dv.transpose(0, 2, 1)) < 5e-3
