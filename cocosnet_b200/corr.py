@@ -90,9 +90,9 @@ def correspondence_tail(theta_conv, phi_conv, ref_img, *, match_kernel=3, pono_c
         ref_seg = F.interpolate(ref_seg_map, scale_factor=1 / down, mode="nearest")
         values.append(ref_seg.reshape(b, ref_seg.shape[1], -1))
     y_all = attend(theta, phi, torch.cat(values, 1) if len(values) > 1 else ref, scale, precision)
-    y = y_all[:, :channel]
+    y = y_all[:, :channel].contiguous() if len(values) > 1 else y_all
     if want_direct:
-        extras["warp_mask"] = y_all[:, channel:].reshape(b, -1, fh, fw)
+        extras["warp_mask"] = y_all[:, channel:].contiguous().reshape(b, -1, fh, fw)
 
     # column softmax == the same primitive with the operands swapped
     if warp_mask_losstype == "cycle" and not want_direct:  # :337-346

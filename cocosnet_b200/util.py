@@ -1,0 +1,82 @@
+"""Small helpers with the reference's semantics (util/util.py)."""
+import importlib
+import os
+import sys
+
+import torch
+
+_EPS = sys.float_info.epsilon
+
+
+def feature_normalize(x):
+    """x / (||x||_2 over dim 1 + eps)   (util/util.py:31-34)."""
+    return x / (torch.norm(x, 2, 1, keepdim=True) + _EPS)
+
+
+def weighted_l1_loss(inp, target, weights):  # util/util.py:36-40
+    return (torch.abs(inp - target) * weights.expand_as(inp)).mean()
+
+
+def mse_loss(inp, target=0):  # util/util.py:42-43
+    return torch.mean((inp - target) ** 2)
+
+
+_VGG_MEAN = (0.40760392, 0.45795686, 0.48501961)
+
+
+def vgg_preprocess(t, vgg_normal_correct=False):
+    """RGB in [0,1] (or [-1,1] with vgg_normal_correct) -> BGR, mean-subtracted,
+    x255 (util/util.py:45-54)."""
+    if vgg_normal_correct:
+        t = (t + 1) / 2
+    bgr = t.flip(1)
+    mean = torch.tensor(_VGG_MEAN, dtype=t.dtype, device=t.device).view(1, 3, 1, 1)
+    return (bgr - mean) * 255
+
+
+def find_class_in_module(target_cls_name, module):
+    """Case-insensitive class lookup by name with '_' removed (util/util.py:211-223)."""
+    target = target_cls_name.replace("_", "").lower()
+    mod = importlib.import_module(module) if isinstance(module, str) else module
+    for name, cls in mod.__dict__.items():
+        if name.lower() == target and isinstance(cls, type):
+            return cls
+    raise ValueError("In %s there should be a class whose lower-case name is %s" % (module, target))
+
+
+def save_network(net, label, epoch, opt):
+    """'<epoch>_net_<label>.pth' plain state_dict (util/util.py:226-231)."""
+    path = os.path.join(opt.checkpoints_dir, opt.name, "%s_net_%s.pth" % (epoch, label))
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, path)
+
+
+def load_network(net, label, epoch, opt):
+    """Tolerant load (util/util.py:234-250): missing file -> untouched net,
+    shape/key mismatch -> strict=False."""
+    path = os.path.join(opt.checkpoints_dir, opt.name, "%s_net_%s.pth" % (epoch, label))
+    if not os.path.exists(path):
+        print("not find model :" + path + ", do not load model!")
+        return net
+    weights = torch.load(path, map_location="cpu")
+    try:
+        net.load_state_dict(weights)
+    except KeyError:
+        print("key error, not load!")
+    except RuntimeError as err:
+        print(err)
+        net.load_state_dict(weights, strict=False)
+        print("loaded with strict=False")
+    return net
+
+
+def print_current_errors(opt, epoch, i, errors, t):  # util/util.py:320-331
+    msg = "(epoch: %d, iters: %d, time: %.3f) " % (epoch, i, t)
+    for k, v in errors.items():
+        msg += "%s: %.3f " % (k, v.mean().float())
+    print(msg)
+    try:
+        with open(os.path.join(opt.checkpoints_dir, opt.name, "loss_log.txt"), "a") as f:
+            f.write("%s\n" % msg)
+    except OSError as err:
+        print(err)
