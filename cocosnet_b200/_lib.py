@@ -25,6 +25,7 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0  # kernels enqueued through the C-ABI (bench.py reports it)
 
 
 class CocosError(RuntimeError):
@@ -54,7 +55,9 @@ def lib():
     return h
 
 
-def check(rc, what):
+def check(rc, what, kernels=1):
+    global LAUNCHES
+    LAUNCHES += kernels
     if rc != 0:
         msg = lib().cocos_last_error()
         raise CocosError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,50 @@
+"""Where does the train step spend its GPU time?  torch.profiler kernel table
+for one G+D step at batch B (after warm-up).  python tools/profile_step.py --b 8"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from cocosnet_b200 import data as cdata  # noqa: E402
+from cocosnet_b200.trainer import Pix2PixTrainer  # noqa: E402
+from oracle import torch_port  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--b", type=int, default=8)
+    ap.add_argument("--rows", type=int, default=45)
+    args = ap.parse_args()
+    opt = bench.make_opt(args.b, gpu=True)
+    torch.manual_seed(0)
+    trainer = Pix2PixTrainer(opt)
+    trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+    batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cdata.synthetic_batch(opt, args.b).items()}
+
+    def step():
+        trainer.run_generator_one_step(batch)
+        trainer.run_discriminator_one_step(batch)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(3):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    print("step ms: %.2f  (%.2f img/s at B=%d)  peak mem %.1f GB" % (s.elapsed_time(e) / 3, args.b * 3e3 / s.elapsed_time(e),
+                                                              args.b, torch.cuda.max_memory_allocated() / 2 ** 30))
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=args.rows, max_name_column_width=70))
+
+
+if __name__ == "__main__":
+    main()
