@@ -15,13 +15,13 @@ _c_int, _c_float, _c_ll, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_longlong, 
 SIGNATURES = {
     "cocos_abi_version": [],
     "cocos_last_error": [],
-    "cocos_pack_rows_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
-    "cocos_pack_v_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
+    "cocos_pack_rows_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "cocos_pack_v_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
     "cocos_corr_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                             _c_float, _vp],
-    "cocos_corr_warp_bwd_ds": [_vp] * 10 + [_c_int] * 8 + [_c_float, _c_float, _vp],
+    "cocos_corr_warp_bwd_ds": [_vp] * 10 + [_c_int] * 8 + [_c_float, _vp],
     "cocos_gemm_f16": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
-                       _c_float, _c_int, _vp],
+                       _c_float, _c_int, _c_int, _vp],
 }
 
 _lib = None

@@ -11,12 +11,13 @@ extern "C" {
 int cocos_abi_version(void) { return COCOS_ABI_VERSION; }
 const char* cocos_last_error(void) { return get_error(); }
 
-int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, void* stream) {
-  return pack_rows_f16_launch(src, dst, B, C, N, Kp, split_mode, static_cast<cudaStream_t>(stream));
+int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, float* rowscale_out,
+                        void* stream) {
+  return pack_rows_f16_launch(src, dst, B, C, N, Kp, split_mode, rowscale_out, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, void* stream) {
-  return pack_v_f16_launch(src, dst, B, Cv, Nk, Cvp, Nkp, static_cast<cudaStream_t>(stream));
+int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16, void* stream) {
+  return pack_v_f16_launch(src, dst, B, Cv, Nk, Cvp, Nkp, bf16, static_cast<cudaStream_t>(stream));
 }
 
 int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
@@ -31,24 +32,24 @@ int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out
 
 int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb, int ldc,
                    long long stride_a, long long stride_b, long long stride_c, float alpha, int accumulate,
-                   void* stream) {
+                   int bf16, void* stream) {
   if (!a || !b || !c) {
     set_error("cocos_gemm_f16: null pointer argument");
     return -1;
   }
   return gemm_f16_launch(a, b, c, batch, M, N, K, lda, ldb, ldc, stride_a, stride_b, stride_c, alpha, accumulate,
-                         static_cast<cudaStream_t>(stream));
+                         bf16, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* rscale,
                            const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
-                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, void* stream) {
-  if (!q || !k || !do16 || !v16 || !d_out || !out || !lse || !ds || !dst) {
+                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, void* stream) {
+  if (!q || !k || !do16 || !v16 || !rscale || !out || !lse || !ds || !dst) {
     set_error("cocos_corr_warp_bwd_ds: null pointer argument");
     return -1;
   }
-  return corr_bwd_ds_launch(q, k, do16, v16, d_out, out, lse, ds, dst, pt, B, Nq, Nk, Kd, Cv, Cvk, Nkp, Nqp, scale,
-                            dscale, static_cast<cudaStream_t>(stream));
+  return corr_bwd_ds_launch(q, k, do16, v16, rscale, out, lse, ds, dst, pt, B, Nq, Nk, Kd, Cv, Cvk, Nkp, Nqp, scale,
+                            static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -2,7 +2,7 @@
 // softmax-Jacobian product
 //     dS[i,j] = P[i,j] * (dP[i,j] - D[i]) * scale,   P = exp(scale*S - lse),
 //     dP = dO V^T,  D[i] = sum_c dO[c,i] O[c,i]
-// as fp16 (pre-multiplied by `dscale` to sit in fp16 range) in BOTH
+// as bf16 (dO enters row-scaled in fp16, the scale is divided back out) in BOTH
 // orientations -- dS [B,Nq,Nkp] and dS^T [B,Nk,Nqp] -- plus optionally P^T.
 // Two plain tcgen05 GEMMs (gemm.cu) then give dQ^T = K^T-major x dS and
 // dK^T = Q^T-major x dS^T; a third gives dV from P^T.  This is what autograd
@@ -15,6 +15,8 @@
 #include "corr_kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
+
+#include <cuda_bf16.h>
 
 namespace cocos {
 
@@ -31,13 +33,14 @@ struct BwdParams {
   int B, Nq, Nk, Kd, Cv, Cvk;
   int kc_count, vc_count, n_tiles, ns;
   int Nkp, Nqp;
-  float scale, scale_log2, dscale;
-  const float* d_out;  // [B, Cv, Nq]
+  float scale, scale_log2;
+  const __half* do16;  // [B, Nq, Cvk] row-scaled dO (the dP operand)
+  const float* rscale; // [B, Nq] the row scale r_i applied to dO
   const float* out;    // [B, Cv, Nq]
   const float* lse;    // [B, Nq]
-  __half* ds;          // [B, Nq, Nkp]
-  __half* dst;         // [B, Nk, Nqp]
-  __half* pt;          // [B, Nk, Nqp] or null
+  uint16_t* ds;        // bf16 [B, Nq, Nkp]
+  uint16_t* dst;       // bf16 [B, Nk, Nqp]
+  uint16_t* pt;        // bf16 [B, Nk, Nqp] or null
 };
 
 struct BwdBars {
@@ -55,7 +58,12 @@ struct BwdBars {
 __device__ __forceinline__ void wg_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // copy a staged 128x128 fp16 tile (pitch TPITCH) to global rows of pitch `gpitch`
-__device__ __forceinline__ void copy_tile_out(const uint8_t* tile, __half* gbase, int gpitch, int valid_rows,
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void copy_tile_out(const uint8_t* tile, uint16_t* gbase, int gpitch, int valid_rows,
                                               int valid_cols, int tid) {
   const int chunk = tid & 15;
   if (chunk * 8 >= valid_cols) return;
@@ -181,15 +189,16 @@ corr_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const bool row_ok = q < p.Nq;
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
     const float c2 = p.scale_log2;
-    float lse2 = INFINITY, dsum = 0.f;
+    // D'[i] = sum_c dO'[i,c] * O[c,i] with the SAME fp16-rounded, row-scaled dO' the dP MMA consumes, so
+    // that sum_j P[i,j] (dP'[i,j] - D'[i]) cancels to rounding noise instead of to an fp16-vs-fp32 bias.
+    float lse2 = INFINITY, dsum = 0.f, gs = 0.f;
     if (row_ok) {
       lse2 = p.lse[static_cast<size_t>(bidx) * p.Nq + q] * 1.4426950408889634f;
-      for (int c = 0; c < p.Cv; ++c) {
-        const size_t idx = (static_cast<size_t>(bidx) * p.Cv + c) * p.Nq + q;
-        dsum = fmaf(p.d_out[idx], p.out[idx], dsum);
-      }
+      const __half* drow = p.do16 + (static_cast<size_t>(bidx) * p.Nq + q) * p.Cvk;
+      for (int c = 0; c < p.Cv; ++c)
+        dsum = fmaf(__half2float(drow[c]), p.out[(static_cast<size_t>(bidx) * p.Cv + c) * p.Nq + q], dsum);
+      gs = p.scale / p.rscale[static_cast<size_t>(bidx) * p.Nq + q];  // undo the row scale: true dS in bf16
     }
-    const float gs = p.scale * p.dscale;
     const int valid_rows = min(BM, p.Nq - q0);
 
     for (int j = 0; j < T; ++j) {
@@ -217,7 +226,7 @@ corr_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int i = 0; i < 32; i += 2) {
           const float d0 = s[c * 32 + i] * (__uint_as_float(r[i]) - dsum) * gs;
           const float d1 = s[c * 32 + i + 1] * (__uint_as_float(r[i + 1]) - dsum) * gs;
-          dsp[(c * 32 + i) >> 1] = pack_h2(d0, d1);
+          dsp[(c * 32 + i) >> 1] = pack_bf2(d0, d1);
         }
       }
       tc_fence_before();
@@ -244,7 +253,7 @@ corr_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (p.pt != nullptr) {
 #pragma unroll
         for (int c = 0; c < BN / 2; ++c) {
-          const uint32_t h = pack_h2(s[2 * c], s[2 * c + 1]);
+          const uint32_t h = pack_bf2(s[2 * c], s[2 * c + 1]);
           *reinterpret_cast<uint16_t*>(tile + ((2 * c) * TPITCH + row) * 2) = static_cast<uint16_t>(h & 0xFFFF);
           *reinterpret_cast<uint16_t*>(tile + ((2 * c + 1) * TPITCH + row) * 2) = static_cast<uint16_t>(h >> 16);
         }
@@ -264,9 +273,9 @@ corr_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 }  // namespace
 
-int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const void* v16, const float* rscale,
                        const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
-                       int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, cudaStream_t stream) {
+                       int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, cudaStream_t stream) {
   if (B <= 0 || Nq <= 0 || Nk <= 0 || Kd <= 0 || (Kd % BK) || Cvk <= 0 || (Cvk % BK) || Cv <= 0 || Cv > Cvk) {
     set_error("corr_bwd_ds: bad shape (B=%d Nq=%d Nk=%d Kd=%d Cv=%d Cvk=%d)", B, Nq, Nk, Kd, Cv, Cvk);
     return -1;
@@ -279,9 +288,9 @@ int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const voi
   p.B = B; p.Nq = Nq; p.Nk = Nk; p.Kd = Kd; p.Cv = Cv; p.Cvk = Cvk;
   p.kc_count = Kd / BK; p.vc_count = Cvk / BK; p.n_tiles = (Nk + BN - 1) / BN;
   p.Nkp = Nkp; p.Nqp = Nqp;
-  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f; p.dscale = dscale;
-  p.d_out = d_out; p.out = out; p.lse = lse;
-  p.ds = static_cast<__half*>(ds); p.dst = static_cast<__half*>(dst); p.pt = static_cast<__half*>(pt);
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.do16 = static_cast<const __half*>(do16); p.rscale = rscale; p.out = out; p.lse = lse;
+  p.ds = static_cast<uint16_t*>(ds); p.dst = static_cast<uint16_t*>(dst); p.pt = static_cast<uint16_t*>(pt);
   const int budget = 227 * 1024 - 1024 - 512;
   const int fixed = 2 * p.vc_count * ATOM_BYTES + TILE_BYTES;
   p.ns = (budget - fixed) / (2 * ATOM_BYTES);

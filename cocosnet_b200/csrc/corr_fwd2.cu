@@ -1,50 +1,41 @@
-// K1: fused correlation -> softmax -> warp for sm_100a.
+// K1 v2: fused correlation -> softmax -> warp with TWO softmax warpgroups.
 //
-//   O[b,c,i] = sum_j softmax_j(scale * <Q[b,i,:], K[b,j,:]>) * V[b,j,c]
+// Same math and operand layouts as corr_fwd.cu; the difference is the
+// pipeline.  The exp throughput (MUFU, 16/clk/SM) is co-critical with the
+// tensor core at C=256, and one warpgroup cannot both keep MUFU busy and hide
+// the TMEM->register->smem latency chain.  Here warpgroup g handles key tiles
+// t = g (mod 2) with its own S buffer, P buffer, running (max, sum) and its
+// own O accumulator in TMEM, so while one group is in its exp loop the other
+// is loading/stashing, and the MMA warp alternates S_t / PV_{t-1}.  The two
+// partial (m, l, O) are merged once at the end through shared memory.
 //
-// Replaces reference correspondence.py:291 (matmul theta^T phi), :304
-// (/temperature), :307 (row softmax) and :318/:334 (matmul with the exemplar /
-// its mask) without ever writing the HWxHW matrix to HBM.
-//
-// One CTA owns 128 query rows and streams 128-key tiles:
-//   warp 4  : TMA producer  (Q once or chunk-streamed, K chunks, V tiles)
-//   warp 5  : tcgen05.mma issuer (S = Q K^T into a double-buffered TMEM tile,
-//             O += P V into a TMEM accumulator), TMEM owner
-//   warps 0-3: online softmax, one thread per query row (TMEM lane): S from
-//             TMEM -> registers, exp2, P as fp16 into 128B-swizzled smem (the A
-//             operand of the second MMA), lazy rescale of O, final epilogue.
+//   warps 0-3 : softmax WG0 (even key tiles)     warp 8 : TMA producer
+//   warps 4-7 : softmax WG1 (odd key tiles)      warp 9 : MMA issuer, TMEM owner
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+Cvp) O1 [384,384+Cvp), Cvp <= 128.
 #include "corr_kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
-
-#include <stdlib.h>
 
 namespace cocos {
 
 namespace {
 
-constexpr int BM = 128;  // queries per CTA
-constexpr int BN = 128;  // keys per tile
-constexpr int BK = 64;   // fp16 elements per 128B swizzle atom row
-constexpr int ATOM_BYTES = 128 * BK * 2;  // 16 KiB: 128 rows x 64 fp16
-constexpr int NUM_THREADS = 192;
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int ATOM_BYTES = 128 * BK * 2;
+constexpr int NUM_THREADS = 320;
 constexpr int MAX_KSTAGES = 8;
 constexpr int MAX_VSTAGES = 2;
-constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units (P stays <= 2^8)
+constexpr float RESCALE_THRESHOLD = 8.0f;
 
-struct FwdParams {
+struct Fwd2Params {
   int B, Nq, Nk, Kd, Cv, Cvp;
-  int kc_count;    // Kd / 64
-  int n_tiles;     // ceil(Nk / 128)
-  int q_resident;  // Q tile kept in smem for the whole CTA
-  int ns_k, ns_v;
+  int kc_count, n_tiles, q_resident, ns_k, ns_v;
   float scale, scale_log2;
-  float* out;   // [B, Cv, Nq]
-  float* lse;   // [B, Nq] (natural log) or null
-  float* corr;  // [B, Nq, Nk] scaled logits or null (return_corr / debug)
+  float* out;
+  float* lse;
 };
 
-struct Barriers {
+struct Bars2 {
   uint64_t q_full;
   uint64_t k_full[MAX_KSTAGES];
   uint64_t k_empty[MAX_KSTAGES];
@@ -52,34 +43,33 @@ struct Barriers {
   uint64_t v_empty[MAX_VSTAGES];
   uint64_t s_full[2];
   uint64_t s_empty[2];
-  uint64_t p_full;
-  uint64_t pv_done;
+  uint64_t p_full[2];
+  uint64_t pv_done[2];
   uint32_t tmem_base;
   uint32_t pad;
+  float merge_m[128];
+  float merge_l[128];
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+corr_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const Fwd2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B swizzle atoms
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const int q0 = blockIdx.x * BM;
-  const int bidx = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BM, bidx = blockIdx.y;
 
   const uint32_t stage_bytes = p.q_resident ? ATOM_BYTES : 2 * ATOM_BYTES;
-  const uint32_t v_stage_bytes = static_cast<uint32_t>(p.Cvp) * 256u;  // 2 atoms of [Cvp x 64] fp16
+  const uint32_t v_stage_bytes = static_cast<uint32_t>(p.Cvp) * 256u;
   const uint32_t q_smem = smem0;
   const uint32_t k_ring = q_smem + (p.q_resident ? p.kc_count * ATOM_BYTES : 0);
   const uint32_t v_ring = k_ring + p.ns_k * stage_bytes;
-  const uint32_t p_smem = v_ring + p.ns_v * v_stage_bytes;
-  const uint32_t bar_off = p_smem + 2 * ATOM_BYTES - smem0;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_gen + bar_off);
+  const uint32_t p_smem = v_ring + p.ns_v * v_stage_bytes;  // P0 | P1, 2 atoms each
+  const uint32_t bar_off = p_smem + 4 * ATOM_BYTES - smem0;
+  Bars2* bars = reinterpret_cast<Bars2*>(smem_gen + bar_off);
+  float* merge_o = reinterpret_cast<float*>(smem_gen + (p_smem - smem0));  // reused after the last MMA
 
   if (tid == 0) {
     mbar_init(smem_u32(&bars->q_full), 1);
@@ -94,17 +84,17 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->s_empty[i]), 128);
+      mbar_init(smem_u32(&bars->p_full[i]), 128);
+      mbar_init(smem_u32(&bars->pv_done[i]), 1);
     }
-    mbar_init(smem_u32(&bars->p_full), 128);
-    mbar_init(smem_u32(&bars->pv_done), 1);
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -112,10 +102,9 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t tmem_o = tmem + 256;  // S0: [0,128) S1: [128,256) O: [256, 256+Cvp)
   const int T = p.n_tiles;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       if (p.q_resident) {
@@ -147,7 +136,7 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(BM, BN);
@@ -158,12 +147,12 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
       }
       auto issue_s = [&](int t) {
-        const int b = t & 1;
-        if (t >= 2) {
-          mbar_wait(smem_u32(&bars->s_empty[b]), ((t >> 1) - 1) & 1);
+        const int g = t & 1, u = t >> 1;
+        if (u >= 1) {
+          mbar_wait(smem_u32(&bars->s_empty[g]), (u - 1) & 1);
           tc_fence_after();
         }
-        const uint32_t d_tmem = tmem + b * BN;
+        const uint32_t d_tmem = tmem + g * BN;
         for (int kc = 0; kc < p.kc_count; ++kc) {
           mbar_wait(smem_u32(&bars->k_full[ks]), kph);
           tc_fence_after();
@@ -171,66 +160,68 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint32_t a_addr = p.q_resident ? (q_smem + kc * ATOM_BYTES) : st;
           const uint32_t b_addr = p.q_resident ? st : (st + ATOM_BYTES);
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
+          for (int s4 = 0; s4 < 4; ++s4)
             umma_f16(d_tmem, make_desc_k_sw128(a_addr + s4 * 32), make_desc_k_sw128(b_addr + s4 * 32), idesc_s,
                      (kc | s4) != 0 ? 1u : 0u);
-          }
           umma_commit(smem_u32(&bars->k_empty[ks]));
           if (++ks == static_cast<uint32_t>(p.ns_k)) { ks = 0; kph ^= 1; }
         }
-        umma_commit(smem_u32(&bars->s_full[b]));
+        umma_commit(smem_u32(&bars->s_full[g]));
       };
-      issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_s(j + 1);
-        mbar_wait(smem_u32(&bars->p_full), j & 1);
+      auto issue_pv = [&](int t) {
+        const int g = t & 1, u = t >> 1;
+        mbar_wait(smem_u32(&bars->p_full[g]), u & 1);
         mbar_wait(smem_u32(&bars->v_full[vs]), vph);
         tc_fence_after();
         const uint32_t vb = v_ring + vs * v_stage_bytes;
+        const uint32_t pb = p_smem + g * 2 * ATOM_BYTES;
 #pragma unroll
         for (int st = 0; st < 8; ++st) {
-          const uint32_t a_addr = p_smem + (st >> 2) * ATOM_BYTES + (st & 3) * 32;
+          const uint32_t a_addr = pb + (st >> 2) * ATOM_BYTES + (st & 3) * 32;
           const uint32_t b_addr = vb + (st >> 2) * (v_stage_bytes / 2) + (st & 3) * 32;
-          umma_f16(tmem_o, make_desc_k_sw128(a_addr), make_desc_k_sw128(b_addr), idesc_pv,
-                   (j | st) != 0 ? 1u : 0u);
+          umma_f16(tmem + 256 + g * 128, make_desc_k_sw128(a_addr), make_desc_k_sw128(b_addr), idesc_pv,
+                   (u | st) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&bars->v_empty[vs]));
-        umma_commit(smem_u32(&bars->pv_done));
+        umma_commit(smem_u32(&bars->pv_done[g]));
         if (++vs == static_cast<uint32_t>(p.ns_v)) { vs = 0; vph ^= 1; }
+      };
+      issue_s(0);
+      for (int t = 1; t < T; ++t) {
+        issue_s(t);
+        issue_pv(t - 1);
       }
+      issue_pv(T - 1);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------- softmax warps (0..3)
-    const int row = tid;  // TMEM lane == query row within the tile
+    // ------------------------------------------- softmax warpgroups (warps 0..7)
+    const int g = warp >> 2;          // warpgroup: even / odd key tiles
+    const int row = tid & 127;        // TMEM lane == query row
     const int q = q0 + row;
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem + g * BN;
+    const uint32_t tmem_o = tmem + 256 + g * 128;
     const float c2 = p.scale_log2;
     float m = -INFINITY, l = 0.f;
-    const uint32_t row_off = p_smem + row * 128;
+    const uint32_t row_off = p_smem + g * 2 * ATOM_BYTES + row * 128;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
+    int n_mine = 0;
 
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      mbar_wait(smem_u32(&bars->s_full[b]), (j >> 1) & 1);
+    for (int t = g; t < T; t += 2) {
+      const int u = t >> 1;
+      ++n_mine;
+      mbar_wait(smem_u32(&bars->s_full[g]), u & 1);
       tc_fence_after();
       float s[BN];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        tmem_ld32(tmem + lane_sel + b * BN + c * 32, reinterpret_cast<uint32_t*>(&s[c * 32]));
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + lane_sel + c * 32, reinterpret_cast<uint32_t*>(&s[c * 32]));
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->s_empty[b]));
+      mbar_arrive(smem_u32(&bars->s_empty[g]));
 
-      if (p.corr != nullptr && q < p.Nq) {
-        float* dst = p.corr + (static_cast<size_t>(bidx) * p.Nq + q) * p.Nk + j * BN;
-        const int valid = p.Nk - j * BN;
-#pragma unroll
-        for (int c = 0; c < BN; ++c)
-          if (c < valid) dst[c] = s[c] * p.scale;
-      }
-      if (j == T - 1 && (p.Nk & (BN - 1)) != 0) {
-        const int valid = p.Nk - j * BN;
+      if (t == T - 1 && (p.Nk & (BN - 1)) != 0) {
+        const int valid = p.Nk - t * BN;
 #pragma unroll
         for (int c = 0; c < BN; ++c)
           if (c >= valid) s[c] = -INFINITY;
@@ -239,7 +230,7 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int c = 1; c < BN; ++c) tmax = fmaxf(tmax, s[c]);
       const float m_new = fmaxf(m, tmax);
-      if (j == 0) {
+      if (u == 0) {
         m = m_new;
       } else {
         const bool resc = (m_new - m) * c2 > RESCALE_THRESHOLD;
@@ -247,7 +238,7 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const float alpha = resc ? ex2((m - m_new) * c2) : 1.0f;
           if (resc) m = m_new;
           l *= alpha;
-          mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
+          mbar_wait(smem_u32(&bars->pv_done[g]), (u - 1) & 1);
           tc_fence_after();
           for (int cc = 0; cc < p.Cvp; cc += 16) {
             uint32_t o[16];
@@ -272,7 +263,7 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         pk[i] = pack_h2(p0, p1);
       }
       l += sum;
-      if (j > 0) mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);  // P buffer free again
+      if (u > 0) mbar_wait(smem_u32(&bars->pv_done[g]), (u - 1) & 1);  // my P buffer is free again
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const uint32_t addr = row_off + (c >> 3) * ATOM_BYTES + (((c & 7) ^ sw) << 4);
@@ -281,32 +272,63 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                      : "memory");
       }
       fence_proxy_async_smem();
-      mbar_arrive(smem_u32(&bars->p_full));
+      mbar_arrive(smem_u32(&bars->p_full[g]));
     }
 
-    // epilogue: O / l -> out[b, c, q]
-    mbar_wait(smem_u32(&bars->pv_done), (T - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    for (int cc = 0; cc < p.Cvp; cc += 16) {
-      uint32_t o[16];
-      tmem_ld16(tmem_o + lane_sel + cc, o);
-      tmem_wait_ld();
-      if (q < p.Nq) {
+    // ---- merge the two partial softmax states; WG0 writes the result
+    if (n_mine > 0) {
+      mbar_wait(smem_u32(&bars->pv_done[g]), (n_mine - 1) & 1);
+      tc_fence_after();
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");  // every MMA has completed: P buffers are reusable
+    if (g == 1) {
+      bars->merge_m[row] = m;
+      bars->merge_l[row] = l;
+      for (int cc = 0; cc < p.Cvp; cc += 16) {
+        uint32_t o[16];
+        if (n_mine > 0) {
+          tmem_ld16(tmem_o + lane_sel + cc, o);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = cc + i;
-          if (c < p.Cv) p.out[(static_cast<size_t>(bidx) * p.Cv + c) * p.Nq + q] = __uint_as_float(o[i]) * inv_l;
+          for (int i = 0; i < 16; ++i) o[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) merge_o[(cc + i) * 128 + row] = __uint_as_float(o[i]);
+      }
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (g == 0) {
+      const float m1 = bars->merge_m[row], l1 = bars->merge_l[row];
+      const float mm = fmaxf(m, m1);
+      const float a0 = ex2((m - mm) * c2);
+      const float a1 = (m1 == -INFINITY) ? 0.f : ex2((m1 - mm) * c2);
+      const float lt = l * a0 + l1 * a1;
+      const float inv_l = 1.0f / lt;
+      for (int cc = 0; cc < p.Cvp; cc += 16) {
+        uint32_t o[16];
+        tmem_ld16(tmem_o + lane_sel + cc, o);
+        tmem_wait_ld();
+        if (q < p.Nq) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cc + i;
+            if (c < p.Cv) {
+              const float v = (__uint_as_float(o[i]) * a0 + merge_o[c * 128 + row] * a1) * inv_l;
+              p.out[(static_cast<size_t>(bidx) * p.Cv + c) * p.Nq + q] = v;
+            }
+          }
         }
       }
+      if (p.lse != nullptr && q < p.Nq)
+        p.lse[static_cast<size_t>(bidx) * p.Nq + q] = (mm * c2 + log2f(lt)) * 0.6931471805599453f;
+      tc_fence_before();
     }
-    if (p.lse != nullptr && q < p.Nq)
-      p.lse[static_cast<size_t>(bidx) * p.Nq + q] = (m * c2 + log2f(l)) * 0.6931471805599453f;
-    tc_fence_before();
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -314,46 +336,17 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
-                         int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream) {
-  if (B <= 0 || Nq <= 0 || Nk <= 0) {
-    set_error("corr_warp_fwd: empty problem (B=%d Nq=%d Nk=%d)", B, Nq, Nk);
-    return -1;
-  }
-  if (Kd <= 0 || (Kd % BK) != 0) {
-    set_error("corr_warp_fwd: Kd=%d must be a positive multiple of 64 (pad in the pack kernel)", Kd);
-    return -1;
-  }
-  if (Cv <= 0 || Cvp < Cv || (Cvp % 16) != 0 || Cvp > 256) {
-    set_error("corr_warp_fwd: need 0 < Cv <= Cvp <= 256, Cvp %% 16 == 0 (Cv=%d Cvp=%d)", Cv, Cvp);
-    return -1;
-  }
-  if (Nkp < Nk || (Nkp % 8) != 0) {
-    set_error("corr_warp_fwd: V row pitch Nkp=%d must be >= Nk=%d and a multiple of 8", Nkp, Nk);
-    return -1;
-  }
-  {
-    // default: two-warpgroup pipeline; COCOS_K1_VARIANT=1 forces the single-warpgroup kernel
-    static const int variant = [] {
-      const char* e = getenv("COCOS_K1_VARIANT");
-      return e ? atoi(e) : 2;
-    }();
-    if (variant == 2 && corr == nullptr && Cvp <= 128) {
-      const int rc2 = corr_warp_fwd2_launch(q, k, vt, out, lse, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale, stream);
-      if (rc2 != 1) return rc2;
-    }
-  }
-  FwdParams p;
+int corr_warp_fwd2_launch(const void* q, const void* k, const void* vt, float* out, float* lse, int B, int Nq,
+                          int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream) {
+  Fwd2Params p;
   p.B = B; p.Nq = Nq; p.Nk = Nk; p.Kd = Kd; p.Cv = Cv; p.Cvp = Cvp;
   p.kc_count = Kd / BK;
   p.n_tiles = (Nk + BN - 1) / BN;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.out = out; p.lse = lse; p.corr = corr;
-
-  // shared memory plan (<= 227 KiB): [Q] [K ring] [V ring] [P] [barriers]
-  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
-  const int p_bytes = 2 * ATOM_BYTES;
+  p.out = out; p.lse = lse;
+  const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(Bars2)) - 64;
+  const int p_bytes = 4 * ATOM_BYTES;
   const int v_stage = Cvp * 256;
   p.q_resident = (Kd <= 256) ? 1 : 0;
   const int q_bytes = p.q_resident ? p.kc_count * ATOM_BYTES : 0;
@@ -366,11 +359,8 @@ int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* ou
   }
   p.ns_k = rem / stage;
   if (p.ns_k > MAX_KSTAGES) p.ns_k = MAX_KSTAGES;
-  if (p.ns_k < 2) {
-    set_error("corr_warp_fwd: shared memory plan failed (Kd=%d Cvp=%d)", Kd, Cvp);
-    return -1;
-  }
-  const int smem_bytes = 1024 + q_bytes + p.ns_k * stage + p.ns_v * v_stage + p_bytes + 512;
+  if (p.ns_k < 2) return 1;  // caller falls back to the single-warpgroup kernel
+  const int smem_bytes = 1024 + q_bytes + p.ns_k * stage + p.ns_v * v_stage + p_bytes + sizeof(Bars2) + 64;
 
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
@@ -378,10 +368,10 @@ int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* ou
   if ((rc = make_tmap_f16_3d(&tm_k, k, Kd, Nk, B, (uint64_t)Kd * 2, (uint64_t)Nk * Kd * 2, BK, BN, 1))) return rc;
   if ((rc = make_tmap_f16_3d(&tm_v, vt, Nk, Cvp, B, (uint64_t)Nkp * 2, (uint64_t)Cvp * Nkp * 2, BK, Cvp, 1)))
     return rc;
-
-  COCOS_CUDA_CHECK(cudaFuncSetAttribute(corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  COCOS_CUDA_CHECK(
+      cudaFuncSetAttribute(corr_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   dim3 grid((Nq + BM - 1) / BM, B);
-  corr_fwd_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_q, tm_k, tm_v, p);
+  corr_fwd2_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_q, tm_k, tm_v, p);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -10,17 +10,22 @@ namespace cocos {
 int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
                          int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
 
+// two-softmax-warpgroup variant (Cvp <= 128, no corr dump); returns 1 if it does not apply
+int corr_warp_fwd2_launch(const void* q, const void* k, const void* vt, float* out, float* lse, int B, int Nq,
+                          int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
+
 // C[b] (MxN fp32, row-major, ldc) = alpha * A[b] (MxK fp16, K contiguous) * B[b]^T (NxK fp16) (+ C if accumulate)
 int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb,
                     int ldc, long long stride_a, long long stride_b, long long stride_c, float alpha,
-                    int accumulate, cudaStream_t stream);
+                    int accumulate, int bf16, cudaStream_t stream);
 
-int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+int corr_bwd_ds_launch(const void* q, const void* k, const void* do16, const void* v16, const float* rscale,
                        const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
-                       int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, cudaStream_t stream);
+                       int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, cudaStream_t stream);
 
 int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
-                         cudaStream_t stream);
-int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, cudaStream_t stream);
+                         float* rowscale_out, cudaStream_t stream);
+int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16,
+                      cudaStream_t stream);
 
 }  // namespace cocos

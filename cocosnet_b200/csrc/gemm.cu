@@ -24,6 +24,7 @@ struct GemmParams {
   long long stride_c;
   float alpha;
   int accumulate;
+  int bf16;
   float* c;
 };
 
@@ -83,7 +84,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     __syncwarp();
   } else if (warp == 5) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BM, BN);
+      const uint32_t idesc = make_idesc_f16(BM, BN, p.bf16 != 0);
       uint32_t st = 0, ph = 0;
       for (int kc = 0; kc < kc_count; ++kc) {
         mbar_wait(smem_u32(&bars->full[st]), ph);
@@ -155,7 +156,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
 int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb,
                     int ldc, long long stride_a, long long stride_b, long long stride_c, float alpha,
-                    int accumulate, cudaStream_t stream) {
+                    int accumulate, int bf16, cudaStream_t stream) {
   if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) {
     set_error("gemm_f16: empty problem (batch=%d M=%d N=%d K=%d)", batch, M, N, K);
     return -1;
@@ -171,7 +172,7 @@ int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, in
   if ((rc = make_tmap_f16_3d(&tm_a, a, K, M, batch, (uint64_t)lda * 2, sa, BK, BM, 1))) return rc;
   if ((rc = make_tmap_f16_3d(&tm_b, b, K, N, batch, (uint64_t)ldb * 2, sb, BK, BN, 1))) return rc;
   GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.stride_c = stride_c; p.alpha = alpha; p.accumulate = accumulate;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.stride_c = stride_c; p.alpha = alpha; p.accumulate = accumulate; p.bf16 = bf16;
   p.c = c;
   const int smem_bytes = 1024 + STAGES * 2 * ATOM_BYTES + 256;
   COCOS_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -9,6 +9,7 @@
 #include "corr_kernels.h"
 #include "tmap.h"
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 namespace cocos {
@@ -20,7 +21,8 @@ constexpr int TN = 32;  // positions per tile
 
 // split_mode 0: [h]; 1: [h, l, h] (query side); 2: [h, h, l] (key side)
 __global__ void __launch_bounds__(256)
-pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int N, int Kp, int split_mode) {
+pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int N, int Kp, int split_mode,
+                 const float* __restrict__ rowscale) {
   __shared__ float tile[TC][TN + 1];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * TC;
@@ -44,7 +46,8 @@ pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C,
     const int n = n0 + nrow + i;
     const int c = c0 + cx;
     if (n < N && c < Kp) {
-      const float x0 = tile[cx][nrow + i], x1 = tile[cx + 1][nrow + i];
+      const float rs = rowscale ? rowscale[static_cast<size_t>(b) * N + n] : 1.0f;
+      const float x0 = tile[cx][nrow + i] * rs, x1 = tile[cx + 1][nrow + i] * rs;
       const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
       const __half2 hi = __halves2half2(h0, h1);
       __half* row = d + static_cast<size_t>(n) * Kt + c;
@@ -62,36 +65,61 @@ pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C,
 }
 
 __global__ void __launch_bounds__(256)
-pack_v_kernel(const float* __restrict__ src, __half* __restrict__ dst, int Cv, int Nk, int Cvp, int Nkp) {
+pack_v_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int Cv, int Nk, int Cvp, int Nkp, int bf16) {
   const int b = blockIdx.z, c = blockIdx.y;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nkp) return;
   float v = 0.f;
   if (c < Cv && n < Nk) v = src[(static_cast<size_t>(b) * Cv + c) * Nk + n];
-  dst[(static_cast<size_t>(b) * Cvp + c) * Nkp + n] = __float2half_rn(v);
+  uint16_t bits;
+  if (bf16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  } else {
+    const __half h = __float2half_rn(v);
+    bits = *reinterpret_cast<const uint16_t*>(&h);
+  }
+  dst[(static_cast<size_t>(b) * Cvp + c) * Nkp + n] = bits;
+}
+
+// r[b,n] = 1 / max_c |src[b,c,n]|  (1 where the column is all zero)
+__global__ void __launch_bounds__(256)
+rowscale_kernel(const float* __restrict__ src, float* __restrict__ r, int C, int N) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* s = src + static_cast<size_t>(b) * C * N + n;
+  float m = 0.f;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, fabsf(s[static_cast<size_t>(c) * N]));
+  r[static_cast<size_t>(b) * N + n] = (m > 0.f && isfinite(m)) ? 1.0f / m : 1.0f;
 }
 
 }  // namespace
 
 int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
-                         cudaStream_t stream) {
+                         float* rowscale_out, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || N <= 0 || Kp < C || (Kp % 2) != 0 || split_mode < 0 || split_mode > 2) {
     set_error("pack_rows_f16: bad arguments (B=%d C=%d N=%d Kp=%d split=%d)", B, C, N, Kp, split_mode);
     return -1;
   }
+  if (rowscale_out != nullptr) {
+    rowscale_kernel<<<dim3((N + 255) / 256, B), 256, 0, stream>>>(src, rowscale_out, C, N);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+  }
   dim3 grid((N + TN - 1) / TN, (Kp + TC - 1) / TC, B);
-  pack_rows_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), C, N, Kp, split_mode);
+  pack_rows_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), C, N, Kp, split_mode, rowscale_out);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, cudaStream_t stream) {
+int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16,
+                      cudaStream_t stream) {
   if (B <= 0 || Cv <= 0 || Nk <= 0 || Cvp < Cv || Nkp < Nk) {
     set_error("pack_v_f16: bad arguments (B=%d Cv=%d Nk=%d Cvp=%d Nkp=%d)", B, Cv, Nk, Cvp, Nkp);
     return -1;
   }
   dim3 grid((Nkp + 255) / 256, Cvp, B);
-  pack_v_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), Cv, Nk, Cvp, Nkp);
+  pack_v_kernel<<<grid, 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), Cv, Nk, Cvp, Nkp, bf16);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

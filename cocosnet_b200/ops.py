@@ -25,16 +25,18 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def pack_rows(x, kp=None, split=0):
-    """fp32 [B,C,N] -> fp16 [B,N,Kt] (see cocos_pack_rows_f16)."""
+def pack_rows(x, kp=None, split=0, rowscale=False):
+    """fp32 [B,C,N] -> fp16 [B,N,Kt] (see cocos_pack_rows_f16).  With rowscale=True every
+    position is scaled by r = 1/max_c|x| first and (packed, r [B,N]) is returned."""
     _req(x, torch.float32, "x")
     b, c, n = x.shape
     kp = round_up(c, 64) if kp is None else kp
     kt = kp * (3 if split else 1)
     out = torch.empty((b, n, kt), dtype=torch.float16, device=x.device)
-    _lib.check(_lib.lib().cocos_pack_rows_f16(x.data_ptr(), out.data_ptr(), b, c, n, kp, split, _stream()),
-               "cocos_pack_rows_f16")
-    return out
+    r = torch.empty((b, n), dtype=torch.float32, device=x.device) if rowscale else None
+    _lib.check(_lib.lib().cocos_pack_rows_f16(x.data_ptr(), out.data_ptr(), b, c, n, kp, split, _ptr(r), _stream()),
+               "cocos_pack_rows_f16", kernels=2 if rowscale else 1)
+    return (out, r) if rowscale else out
 
 
 def pack_v(v):
@@ -43,7 +45,7 @@ def pack_v(v):
     b, cv, nk = v.shape
     cvp, nkp = round_up(cv, 16), round_up(nk, 8)
     out = torch.empty((b, cvp, nkp), dtype=torch.float16, device=v.device)
-    _lib.check(_lib.lib().cocos_pack_v_f16(v.data_ptr(), out.data_ptr(), b, cv, nk, cvp, nkp, _stream()),
+    _lib.check(_lib.lib().cocos_pack_v_f16(v.data_ptr(), out.data_ptr(), b, cv, nk, cvp, nkp, 0, _stream()),
                "cocos_pack_v_f16")
     return out
 
@@ -67,9 +69,10 @@ def corr_warp_fwd(q16, k16, vt16, cv, nk, scale, want_lse=True, want_corr=False)
 
 
 def _req_rows(t, name):
-    """fp16 CUDA tensor [b, R, C] with unit inner stride (row pitch / batch stride free)."""
-    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float16 and t.dim() == 3 and t.stride(2) == 1):
-        raise _lib.CocosError("%s must be a CUDA fp16 [b,R,C] tensor with contiguous rows" % name)
+    """fp16/bf16 CUDA tensor [b, R, C] with unit inner stride (row pitch / batch stride free)."""
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype in (torch.float16, torch.bfloat16) and t.dim() == 3
+            and t.stride(2) == 1):
+        raise _lib.CocosError("%s must be a CUDA fp16/bf16 [b,R,C] tensor with contiguous rows" % name)
 
 
 def gemm_f16(a16, b16, alpha=1.0, out=None, accumulate=False):
@@ -79,41 +82,43 @@ def gemm_f16(a16, b16, alpha=1.0, out=None, accumulate=False):
     _req_rows(b16, "b16")
     bt, m, k = a16.shape
     n = b16.shape[1]
-    if b16.shape[0] != bt or b16.shape[2] != k:
-        raise _lib.CocosError("gemm_f16: inconsistent shapes %s %s" % (a16.shape, b16.shape))
+    if b16.shape[0] != bt or b16.shape[2] != k or a16.dtype != b16.dtype:
+        raise _lib.CocosError("gemm_f16: inconsistent operands %s %s %s %s" % (a16.shape, b16.shape, a16.dtype,
+                                                                               b16.dtype))
     if out is None:
         out = torch.empty((bt, m, n), dtype=torch.float32, device=a16.device)
     else:
         _req(out, torch.float32, "out")
     _lib.check(_lib.lib().cocos_gemm_f16(a16.data_ptr(), b16.data_ptr(), out.data_ptr(), bt, m, n, k,
                                          a16.stride(1), b16.stride(1), n, a16.stride(0), b16.stride(0), m * n,
-                                         float(alpha), int(bool(accumulate)), _stream()), "cocos_gemm_f16")
+                                         float(alpha), int(bool(accumulate)), int(a16.dtype == torch.bfloat16),
+                                         _stream()), "cocos_gemm_f16")
     return out
 
 
-def cast_rows_f16(x):
-    """fp32 [B,R,C] -> fp16 [B,R,C] view of a buffer whose row pitch is a multiple of 8."""
+def cast_rows(x, dtype=torch.float16):
+    """fp32 [B,R,C] -> fp16/bf16 [B,R,C] view of a buffer whose row pitch is a multiple of 8."""
     _req(x, torch.float32, "x")
     b, r, c = x.shape
     cp = round_up(c, 8)
-    buf = torch.empty((b, r, cp), dtype=torch.float16, device=x.device)
-    _lib.check(_lib.lib().cocos_pack_v_f16(x.data_ptr(), buf.data_ptr(), b, r, c, r, cp, _stream()),
-               "cocos_pack_v_f16")
+    buf = torch.empty((b, r, cp), dtype=dtype, device=x.device)
+    _lib.check(_lib.lib().cocos_pack_v_f16(x.data_ptr(), buf.data_ptr(), b, r, c, r, cp,
+                                           int(dtype == torch.bfloat16), _stream()), "cocos_pack_v_f16")
     return buf[:, :, :c]
 
 
-def corr_warp_bwd_ds(q16, k16, do16, v16, d_out, out, lse, cv, scale, dscale, want_pt):
-    """K1 backward stage A -> (ds [B,Nq,Nk], dst [B,Nk,Nq], pt | None) fp16 (pitched views)."""
+def corr_warp_bwd_ds(q16, k16, do16, rscale, v16, out, lse, cv, scale, want_pt):
+    """K1 backward stage A -> (ds [B,Nq,Nk], dst [B,Nk,Nq], pt | None) bf16 (pitched views)."""
     b, nq, kd = q16.shape
     nk = k16.shape[1]
     cvk = do16.shape[2]
     nkp, nqp = round_up(nk, 8), round_up(nq, 8)
     dev = q16.device
-    ds = torch.empty((b, nq, nkp), dtype=torch.float16, device=dev)
-    dst = torch.empty((b, nk, nqp), dtype=torch.float16, device=dev)
-    pt = torch.empty((b, nk, nqp), dtype=torch.float16, device=dev) if want_pt else None
+    ds = torch.empty((b, nq, nkp), dtype=torch.bfloat16, device=dev)
+    dst = torch.empty((b, nk, nqp), dtype=torch.bfloat16, device=dev)
+    pt = torch.empty((b, nk, nqp), dtype=torch.bfloat16, device=dev) if want_pt else None
     _lib.check(_lib.lib().cocos_corr_warp_bwd_ds(q16.data_ptr(), k16.data_ptr(), do16.data_ptr(), v16.data_ptr(),
-                                                 d_out.data_ptr(), out.data_ptr(), lse.data_ptr(), ds.data_ptr(),
+                                                 rscale.data_ptr(), out.data_ptr(), lse.data_ptr(), ds.data_ptr(),
                                                  dst.data_ptr(), _ptr(pt), b, nq, nk, kd, cv, cvk, nkp, nqp,
-                                                 float(scale), float(dscale), _stream()), "cocos_corr_warp_bwd_ds")
+                                                 float(scale), _stream()), "cocos_corr_warp_bwd_ds")
     return ds[:, :, :nk], dst[:, :, :nq], (pt[:, :, :nq] if want_pt else None)

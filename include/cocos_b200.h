@@ -30,13 +30,17 @@ const char* cocos_last_error(void);
  * fp16 [B, N, Kt], Kt = Kp * (split_mode ? 3 : 1), Kp >= C zero padded, Kp%2==0.
  * This is the `theta.permute(0, 2, 1)` of correspondence.py:281 plus the
  * operand rounding.  split_mode: 0 = plain fp16; 1 = query side [hi, lo, hi];
- * 2 = key side [hi, hi, lo] (one GEMM then sums hi*hi + lo*hi + hi*lo). */
-int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, void* stream);
+ * 2 = key side [hi, hi, lo] (one GEMM then sums hi*hi + lo*hi + hi*lo).
+ * rowscale_out (may be NULL): if given, every position n is first multiplied by
+ * r[b,n] = 1 / max_c |src[b,c,n]| and r is written to rowscale_out [B,N] (used for
+ * the upstream gradient dO in the backward so it always fits fp16). */
+int cocos_pack_rows_f16(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode, float* rowscale_out,
+                        void* stream);
 
 /* fp32 [B, Cv, Nk] (channel-major exemplar values: avg-pooled ref image
  * correspondence.py:313-315, unfolded patches :311, ref_seg :330-332) ->
- * fp16 [B, Cvp, Nkp], zero padded; Cvp % 16 == 0, Nkp % 8 == 0. */
-int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, void* stream);
+ * fp16 (bf16 if `bf16` != 0) [B, Cvp, Nkp], zero padded; for K1: Cvp % 16 == 0, Nkp % 8 == 0. */
+int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16, void* stream);
 
 /* K1, fused correlation + softmax + warp.  Replaces
  *   f = matmul(theta_permute, phi)          correspondence.py:291
@@ -55,25 +59,26 @@ int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out
                         int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, void* stream);
 
 /* Batched tcgen05 GEMM: C[b] (MxN fp32 row-major, ldc) = alpha * A[b] (MxK fp16,
- * K contiguous, lda) * B[b]^T (NxK fp16, ldb) (+ C[b] if accumulate).  Strides in
+ * K contiguous, lda) * B[b]^T (NxK fp16, ldb) (+ C[b] if accumulate); `bf16` != 0
+ * treats both operands as bf16.  Strides in
  * elements.  The torch.matmul / 1x1-conv call sites of correspondence.py:291
  * (return_corr), architecture.py:116-125 and the K1 backward. */
 int cocos_gemm_f16(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb, int ldc,
                    long long stride_a, long long stride_b, long long stride_c, float alpha, int accumulate,
-                   void* stream);
+                   int bf16, void* stream);
 
 /* K1 backward, stage A (what autograd does through correspondence.py:291-318):
- * recomputes S = q k^T and dP = dO V^T tile by tile and writes
- *   ds  fp16 [B, Nq, Nkp] = dscale * P * (dP - D) * scale,  D[i] = sum_c dO[c,i] O[c,i]
- *   dst fp16 [B, Nk, Nqp] = ds^T,   pt fp16 [B, Nk, Nqp] = P^T (optional, may be NULL)
- * q,k as in cocos_corr_warp_fwd; do16 fp16 [B,Nq,Cvk] / v16 fp16 [B,Nk,Cvk] are dO / V
- * position-major (cocos_pack_rows_f16, Cvk % 64 == 0); d_out,out fp32 [B,Cv,Nq]; lse
- * from the forward.  The input gradients then follow from three cocos_gemm_f16 calls:
- *   dq^T[Kd,Nq] = k_cm[Kd,Nk] x ds,  dk^T[Kd,Nk] = q_cm[Kd,Nq] x dst,  dv^T[Cv,Nk] = do_cm[Cv,Nq] x pt,
- * each with alpha = 1/dscale (dv: alpha = 1). */
-int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* d_out,
+ * recomputes S = q k^T and dP' = dO' V^T tile by tile and writes, as bf16,
+ *   ds  [B, Nq, Nkp] = P * (dP' - D') * scale / r,   D'[i] = sum_c dO'[i,c] O[c,i]
+ *   dst [B, Nk, Nqp] = ds^T,   pt [B, Nk, Nqp] = P^T (optional, may be NULL)
+ * q,k as in cocos_corr_warp_fwd; do16 fp16 [B,Nq,Cvk] = row-scaled upstream gradient
+ * dO' = r * dO with rscale = r [B,Nq] (cocos_pack_rows_f16 with rowscale_out), v16 fp16
+ * [B,Nk,Cvk] = V position-major (Cvk % 64 == 0); out fp32 [B,Cv,Nq] and lse from the
+ * forward.  The input gradients follow from three bf16 cocos_gemm_f16 calls:
+ *   dq^T[Kd,Nq] = k_cm[Kd,Nk] x ds,  dk^T[Kd,Nk] = q_cm[Kd,Nq] x dst,  dv^T[Cv,Nk] = do_cm[Cv,Nq] x pt. */
+int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const void* v16, const float* rscale,
                            const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
-                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, float dscale, void* stream);
+                           int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, void* stream);
 
 #ifdef __cplusplus
 }
