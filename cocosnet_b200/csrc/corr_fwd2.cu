@@ -9,8 +9,14 @@
 // is loading/stashing, and the MMA warp alternates S_t / PV_{t-1}.  The two
 // partial (m, l, O) are merged once at the end through shared memory.
 //
-//   warps 0-3 : softmax WG0 (even key tiles)     warp 8 : TMA producer
-//   warps 4-7 : softmax WG1 (odd key tiles)      warp 9 : MMA issuer, TMEM owner
+//   warps 0-3 : softmax WG0 (even key tiles)     warp 8 : TMA producer for Q / K chunks
+//   warps 4-7 : softmax WG1 (odd key tiles)      warp 9 : TMA producer for V tiles
+//   warp 10   : issuer of the S = Q K^T MMAs, TMEM owner
+//   warp 11   : issuer of the O += P V MMAs
+// Two issuers so that the S stream never stalls behind a P tile that is still
+// being exponentiated; descriptors are advanced with one add per MMA and the
+// issue loops are warp-converged (elect.sync) -- the issue path, not the tensor
+// pipe, was the limiter of the first version (profiles/r01_k1_fwd_v1_ncu.md).
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+Cvp) O1 [384,384+Cvp), Cvp <= 128.
 #include "corr_kernels.h"
 #include "ptx.cuh"
@@ -22,9 +28,9 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int ATOM_BYTES = 128 * BK * 2;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 384;
 constexpr int MAX_KSTAGES = 8;
-constexpr int MAX_VSTAGES = 2;
+constexpr int MAX_VSTAGES = 4;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
 struct Fwd2Params {
@@ -92,9 +98,9 @@ corr_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
   }
-  if (warp == 9) {
+  if (warp == 9 && lane == 0) tma_prefetch_desc(&tm_v);
+  if (warp == 10) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -104,98 +110,105 @@ corr_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const uint32_t tmem = bars->tmem_base;
   const int T = p.n_tiles;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if (p.q_resident) {
-        mbar_expect_tx(smem_u32(&bars->q_full), p.kc_count * ATOM_BYTES);
-        for (int kc = 0; kc < p.kc_count; ++kc)
-          tma_load_3d(q_smem + kc * ATOM_BYTES, &tm_q, smem_u32(&bars->q_full), kc * BK, q0, bidx);
-      }
-      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-      for (int j = 0; j < T; ++j) {
-        for (int kc = 0; kc < p.kc_count; ++kc) {
-          mbar_wait(smem_u32(&bars->k_empty[ks]), kph ^ 1);
-          const uint32_t full = smem_u32(&bars->k_full[ks]);
-          mbar_expect_tx(full, stage_bytes);
-          uint32_t dst = k_ring + ks * stage_bytes;
-          if (!p.q_resident) {
-            tma_load_3d(dst, &tm_q, full, kc * BK, q0, bidx);
-            dst += ATOM_BYTES;
+  if (warp >= 8) {
+    setmaxnreg_dec<48>();
+    const bool leader = elect_one();
+    if (warp == 8) {
+      // ------------------------------------------------------ TMA producer: Q, K
+      if (leader) {
+        if (p.q_resident) {
+          mbar_expect_tx(smem_u32(&bars->q_full), p.kc_count * ATOM_BYTES);
+          for (int kc = 0; kc < p.kc_count; ++kc)
+            tma_load_3d(q_smem + kc * ATOM_BYTES, &tm_q, smem_u32(&bars->q_full), kc * BK, q0, bidx);
+        }
+        uint32_t ks = 0, kph = 0;
+        for (int j = 0; j < T; ++j) {
+          for (int kc = 0; kc < p.kc_count; ++kc) {
+            mbar_wait(smem_u32(&bars->k_empty[ks]), kph ^ 1);
+            const uint32_t full = smem_u32(&bars->k_full[ks]);
+            mbar_expect_tx(full, stage_bytes);
+            uint32_t dst = k_ring + ks * stage_bytes;
+            if (!p.q_resident) {
+              tma_load_3d(dst, &tm_q, full, kc * BK, q0, bidx);
+              dst += ATOM_BYTES;
+            }
+            tma_load_3d(dst, &tm_k, full, kc * BK, j * BN, bidx);
+            if (++ks == static_cast<uint32_t>(p.ns_k)) { ks = 0; kph ^= 1; }
           }
-          tma_load_3d(dst, &tm_k, full, kc * BK, j * BN, bidx);
-          if (++ks == static_cast<uint32_t>(p.ns_k)) { ks = 0; kph ^= 1; }
         }
-        mbar_wait(smem_u32(&bars->v_empty[vs]), vph ^ 1);
-        const uint32_t vfull = smem_u32(&bars->v_full[vs]);
-        mbar_expect_tx(vfull, v_stage_bytes);
-        const uint32_t vdst = v_ring + vs * v_stage_bytes;
-        tma_load_3d(vdst, &tm_v, vfull, j * BN, 0, bidx);
-        tma_load_3d(vdst + v_stage_bytes / 2, &tm_v, vfull, j * BN + BK, 0, bidx);
-        if (++vs == static_cast<uint32_t>(p.ns_v)) { vs = 0; vph ^= 1; }
       }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    } else if (warp == 9) {
+      // --------------------------------------------------------- TMA producer: V
+      if (leader) {
+        uint32_t vs = 0, vph = 0;
+        for (int j = 0; j < T; ++j) {
+          mbar_wait(smem_u32(&bars->v_empty[vs]), vph ^ 1);
+          const uint32_t vfull = smem_u32(&bars->v_full[vs]);
+          mbar_expect_tx(vfull, v_stage_bytes);
+          const uint32_t vdst = v_ring + vs * v_stage_bytes;
+          tma_load_3d(vdst, &tm_v, vfull, j * BN, 0, bidx);
+          tma_load_3d(vdst + v_stage_bytes / 2, &tm_v, vfull, j * BN + BK, 0, bidx);
+          if (++vs == static_cast<uint32_t>(p.ns_v)) { vs = 0; vph ^= 1; }
+        }
+      }
+    } else if (warp == 10) {
+      // ------------------------------------------------ MMA issuer: S = Q K^T
       const uint32_t idesc_s = make_idesc_f16(BM, BN);
-      const uint32_t idesc_pv = make_idesc_f16(BM, p.Cvp);
-      uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-      if (p.q_resident) {
-        mbar_wait(smem_u32(&bars->q_full), 0);
-        tc_fence_after();
-      }
-      auto issue_s = [&](int t) {
+      uint32_t ks = 0, kph = 0;
+      if (p.q_resident) mbar_wait(smem_u32(&bars->q_full), 0);
+      for (int t = 0; t < T; ++t) {
         const int g = t & 1, u = t >> 1;
-        if (u >= 1) {
-          mbar_wait(smem_u32(&bars->s_empty[g]), (u - 1) & 1);
-          tc_fence_after();
-        }
+        if (u >= 1) mbar_wait(smem_u32(&bars->s_empty[g]), (u - 1) & 1);
+        tc_fence_after();
         const uint32_t d_tmem = tmem + g * BN;
         for (int kc = 0; kc < p.kc_count; ++kc) {
           mbar_wait(smem_u32(&bars->k_full[ks]), kph);
           tc_fence_after();
-          const uint32_t st = k_ring + ks * stage_bytes;
-          const uint32_t a_addr = p.q_resident ? (q_smem + kc * ATOM_BYTES) : st;
-          const uint32_t b_addr = p.q_resident ? st : (st + ATOM_BYTES);
+          if (leader) {
+            const uint32_t st = k_ring + ks * stage_bytes;
+            const uint64_t da = make_desc_k_sw128(p.q_resident ? (q_smem + kc * ATOM_BYTES) : st);
+            const uint64_t db = make_desc_k_sw128(p.q_resident ? st : (st + ATOM_BYTES));
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4)
-            umma_f16(d_tmem, make_desc_k_sw128(a_addr + s4 * 32), make_desc_k_sw128(b_addr + s4 * 32), idesc_s,
-                     (kc | s4) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&bars->k_empty[ks]));
+            for (int s4 = 0; s4 < 4; ++s4)
+              umma_f16(d_tmem, desc_advance_k16(da, s4), desc_advance_k16(db, s4), idesc_s, (kc | s4) != 0 ? 1u : 0u);
+            umma_commit(smem_u32(&bars->k_empty[ks]));
+            if (kc == p.kc_count - 1) umma_commit(smem_u32(&bars->s_full[g]));
+          }
+          __syncwarp();
           if (++ks == static_cast<uint32_t>(p.ns_k)) { ks = 0; kph ^= 1; }
         }
-        umma_commit(smem_u32(&bars->s_full[g]));
-      };
-      auto issue_pv = [&](int t) {
+      }
+    } else {
+      // ------------------------------------------------ MMA issuer: O += P V
+      const uint32_t idesc_pv = make_idesc_f16(BM, p.Cvp);
+      uint32_t vs = 0, vph = 0;
+      for (int t = 0; t < T; ++t) {
         const int g = t & 1, u = t >> 1;
         mbar_wait(smem_u32(&bars->p_full[g]), u & 1);
         mbar_wait(smem_u32(&bars->v_full[vs]), vph);
         tc_fence_after();
-        const uint32_t vb = v_ring + vs * v_stage_bytes;
-        const uint32_t pb = p_smem + g * 2 * ATOM_BYTES;
+        if (leader) {
+          const uint32_t vb = v_ring + vs * v_stage_bytes;
+          const uint32_t pb = p_smem + g * 2 * ATOM_BYTES;
 #pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          const uint32_t a_addr = pb + (st >> 2) * ATOM_BYTES + (st & 3) * 32;
-          const uint32_t b_addr = vb + (st >> 2) * (v_stage_bytes / 2) + (st & 3) * 32;
-          umma_f16(tmem + 256 + g * 128, make_desc_k_sw128(a_addr), make_desc_k_sw128(b_addr), idesc_pv,
-                   (u | st) != 0 ? 1u : 0u);
+          for (int at = 0; at < 2; ++at) {
+            const uint64_t da = make_desc_k_sw128(pb + at * ATOM_BYTES);
+            const uint64_t db = make_desc_k_sw128(vb + at * (v_stage_bytes / 2));
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4)
+              umma_f16(tmem + 256 + g * 128, desc_advance_k16(da, s4), desc_advance_k16(db, s4), idesc_pv,
+                       (u | at | s4) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bars->v_empty[vs]));
+          umma_commit(smem_u32(&bars->pv_done[g]));
         }
-        umma_commit(smem_u32(&bars->v_empty[vs]));
-        umma_commit(smem_u32(&bars->pv_done[g]));
+        __syncwarp();
         if (++vs == static_cast<uint32_t>(p.ns_v)) { vs = 0; vph ^= 1; }
-      };
-      issue_s(0);
-      for (int t = 1; t < T; ++t) {
-        issue_s(t);
-        issue_pv(t - 1);
       }
-      issue_pv(T - 1);
     }
-    __syncwarp();
   } else {
     // ------------------------------------------- softmax warpgroups (warps 0..7)
+    setmaxnreg_inc<208>();
     const int g = warp >> 2;          // warpgroup: even / odd key tiles
     const int row = tid & 127;        // TMEM lane == query row
     const int q = q0 + row;
@@ -328,7 +341,7 @@ corr_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -351,7 +364,7 @@ int corr_warp_fwd2_launch(const void* q, const void* k, const void* vt, float* o
   p.q_resident = (Kd <= 256) ? 1 : 0;
   const int q_bytes = p.q_resident ? p.kc_count * ATOM_BYTES : 0;
   const int stage = p.q_resident ? ATOM_BYTES : 2 * ATOM_BYTES;
-  p.ns_v = 2;
+  p.ns_v = (v_stage <= 8192) ? 4 : 2;
   int rem = budget - p_bytes - q_bytes - p.ns_v * v_stage;
   if (rem / stage < 3) {
     p.ns_v = 1;

@@ -83,24 +83,25 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BM, BN, p.bf16 != 0);
-      uint32_t st = 0, ph = 0;
-      for (int kc = 0; kc < kc_count; ++kc) {
-        mbar_wait(smem_u32(&bars->full[st]), ph);
-        tc_fence_after();
+    // warp-converged issue loop: every lane polls the barrier, one elected lane issues
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(BM, BN, p.bf16 != 0);
+    uint32_t st = 0, ph = 0;
+    for (int kc = 0; kc < kc_count; ++kc) {
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t a_addr = smem0 + st * 2 * ATOM_BYTES;
-        const uint32_t b_addr = a_addr + ATOM_BYTES;
+        const uint64_t da = make_desc_k_sw128(a_addr), db = make_desc_k_sw128(a_addr + ATOM_BYTES);
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4)
-          umma_f16(tmem, make_desc_k_sw128(a_addr + s4 * 32), make_desc_k_sw128(b_addr + s4 * 32), idesc,
-                   (kc | s4) != 0 ? 1u : 0u);
+          umma_f16(tmem, desc_advance_k16(da, s4), desc_advance_k16(db, s4), idesc, (kc | s4) != 0 ? 1u : 0u);
         umma_commit(smem_u32(&bars->empty[st]));
-        if (++st == STAGES) { st = 0; ph ^= 1; }
+        if (kc == kc_count - 1) umma_commit(smem_u32(&bars->acc_full));
       }
-      umma_commit(smem_u32(&bars->acc_full));
+      __syncwarp();
+      if (++st == STAGES) { st = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else {
     const int row = m0 + tid;
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;

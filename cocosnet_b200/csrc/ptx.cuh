@@ -166,6 +166,28 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16 = 
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// descriptor for the next 16-element K step inside a 128B swizzle atom (+32 bytes)
+__device__ __forceinline__ uint64_t desc_advance_k16(uint64_t d, int steps) { return d + static_cast<uint64_t>(2 * steps); }
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

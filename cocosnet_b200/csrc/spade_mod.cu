@@ -1,0 +1,153 @@
+// Fused PONO + SPADE modulation + LeakyReLU + reflection pad (HBM bound).
+//
+//   y = pad_reflect( lrelu( (x - mean_c) / sqrt(var_c + eps) * (1 + gamma) + beta ) )
+//
+// replaces, per SPADE layer, reference normalization.py:63-68 (PositionalNorm2d,
+// unbiased variance over channels per pixel), :149 (x_hat * (1 + gamma) + beta),
+// architecture.py:94-95 (leaky_relu 0.2) and the nn.ReflectionPad2d in front of
+// the following 3x3 conv (architecture.py:31,73-74): ~11 elementwise launches
+// and as many full-activation HBM round trips in forward, ~20 in backward,
+// become one kernel each way.
+//
+// Layout NCHW fp32.  One thread per (padded) output pixel; the channel loop
+// strides by H*W so a warp reads 32 consecutive pixels of one channel
+// (coalesced).  gamma/beta come as one tensor gb [B, 2C, H, W] (the gamma and
+// beta convs share their input and run as one conv with concatenated filters).
+// Algorithmic bytes per element of x: forward 4 (x) + 8 (gamma,beta) + 4 (y)
+// = 16 B; backward 4 (dy) + 4 (x) + 8 (gb) + 4 (dx) + 8 (dgb) = 28 B.
+#include "corr_kernels.h"
+#include "tmap.h"
+
+namespace cocos {
+
+namespace {
+
+__device__ __forceinline__ int reflect(int i, int n) {
+  // index into [0, n) of padded coordinate i in [-pad, n + pad)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+spade_mod_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gb, float* __restrict__ y,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int H, int W, int pad,
+                     float slope, float eps) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.y;
+  const int op = blockIdx.x * blockDim.x + threadIdx.x;  // padded output pixel
+  if (op >= Hp * Wp) return;
+  const int ho = op / Wp, wo = op - ho * Wp;
+  const int hs = reflect(ho - pad, H), ws = reflect(wo - pad, W);
+  const size_t hw = static_cast<size_t>(H) * W;
+  const size_t pix = static_cast<size_t>(hs) * W + ws;
+  const float* xp = x + static_cast<size_t>(b) * C * hw + pix;
+  const float* gp = gb + static_cast<size_t>(b) * 2 * C * hw + pix;
+  float sum = 0.f;
+  for (int c = 0; c < C; ++c) sum += xp[c * hw];
+  const float mean = sum / C;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = xp[c * hw] - mean;
+    ss = fmaf(d, d, ss);
+  }
+  const float rstd = rsqrtf(ss / (C - 1) + eps);
+  if (ho - pad == hs && wo - pad == ws) {  // interior pixel: owns the saved statistics
+    mean_out[static_cast<size_t>(b) * hw + pix] = mean;
+    rstd_out[static_cast<size_t>(b) * hw + pix] = rstd;
+  }
+  float* yp = y + static_cast<size_t>(b) * C * Hp * Wp + op;
+  const size_t hwp = static_cast<size_t>(Hp) * Wp;
+  for (int c = 0; c < C; ++c) {
+    const float xh = (xp[c * hw] - mean) * rstd;
+    float z = fmaf(xh, 1.0f + gp[c * hw], gp[(C + c) * hw]);
+    z = z > 0.f ? z : z * slope;
+    yp[c * hwp] = z;
+  }
+}
+
+// gradient of the padded output folded back onto source pixel (h, w)
+__device__ __forceinline__ float folded_dy(const float* __restrict__ dyc, int h, int w, int H, int W, int pad,
+                                           int Wp) {
+  // padded coordinates whose reflection source is h: h+pad, and the mirror images
+  int hc[3], wc[3], nh = 0, nw = 0;
+  hc[nh++] = h + pad;
+  if (h >= 1 && h <= pad) hc[nh++] = pad - h;
+  if (h <= H - 2 && h >= H - 1 - pad) hc[nh++] = 2 * (H - 1) - h + pad;
+  wc[nw++] = w + pad;
+  if (w >= 1 && w <= pad) wc[nw++] = pad - w;
+  if (w <= W - 2 && w >= W - 1 - pad) wc[nw++] = 2 * (W - 1) - w + pad;
+  float acc = 0.f;
+  for (int i = 0; i < nh; ++i)
+    for (int j = 0; j < nw; ++j) acc += dyc[static_cast<size_t>(hc[i]) * Wp + wc[j]];
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+spade_mod_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gb,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dx,
+                     float* __restrict__ dgb, int C, int H, int W, int pad, float slope) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t hw = static_cast<size_t>(H) * W;
+  if (pix >= static_cast<int>(hw)) return;
+  const int h = pix / W, w = pix - h * W;
+  const size_t hwp = static_cast<size_t>(Hp) * Wp;
+  const float* xp = x + static_cast<size_t>(b) * C * hw + pix;
+  const float* gp = gb + static_cast<size_t>(b) * 2 * C * hw + pix;
+  const float* dyb = dy + static_cast<size_t>(b) * C * hwp;
+  float* dxp = dx + static_cast<size_t>(b) * C * hw + pix;
+  float* dgp = dgb + static_cast<size_t>(b) * 2 * C * hw + pix;
+  const float mean = mean_in[static_cast<size_t>(b) * hw + pix];
+  const float rstd = rstd_in[static_cast<size_t>(b) * hw + pix];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float xh = (xp[c * hw] - mean) * rstd;
+    const float g1 = 1.0f + gp[c * hw];
+    const float z = fmaf(xh, g1, gp[(C + c) * hw]);
+    float dz = pad ? folded_dy(dyb + c * hwp, h, w, H, W, pad, Wp) : dyb[c * hwp + pix];
+    dz = z > 0.f ? dz : dz * slope;
+    dgp[c * hw] = dz * xh;        // d gamma
+    dgp[(C + c) * hw] = dz;       // d beta
+    const float dxh = dz * g1;
+    dxp[c * hw] = dxh;            // stash; finished in the second pass
+    s1 += dxh;
+    s2 = fmaf(dxh, xh, s2);
+  }
+  const float m1 = s1 / C, m2 = s2 / (C - 1);
+  for (int c = 0; c < C; ++c) {
+    const float xh = (xp[c * hw] - mean) * rstd;
+    dxp[c * hw] = rstd * (dxp[c * hw] - m1 - xh * m2);
+  }
+}
+
+}  // namespace
+
+int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
+                         int W, int pad, float slope, float eps, cudaStream_t stream) {
+  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0) {
+    set_error("spade_mod_fwd: bad shape (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+    return -1;
+  }
+  const int npix = (H + 2 * pad) * (W + 2 * pad);
+  spade_mod_fwd_kernel<<<dim3((npix + 255) / 256, B), 256, 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope,
+                                                                        eps);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
+                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope,
+                         cudaStream_t stream) {
+  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0) {
+    set_error("spade_mod_bwd: bad shape (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+    return -1;
+  }
+  spade_mod_bwd_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, stream>>>(dy, x, gb, mean, rstd, dx, dgb, C, H, W,
+                                                                         pad, slope);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cocos

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torch.nn.utils import spectral_norm
 
 from .. import corr as _corr
+from .. import ops as _ops
 
 
 class BaseNetwork(nn.Module):
@@ -142,17 +143,23 @@ class SPADE(nn.Module):
     def gamma_beta(self, x, segmap):
         segmap = F.interpolate(segmap, size=x.size()[2:], mode="nearest")
         actv = self.pad(self.mlp_shared(segmap))
-        # gamma and beta share their input: one conv with concatenated filters
+        # gamma and beta share their input: one conv with concatenated filters -> gb = [gamma ; beta]
         w = torch.cat((self.mlp_gamma.weight, self.mlp_beta.weight), 0)
         b = torch.cat((self.mlp_gamma.bias, self.mlp_beta.bias), 0)
-        gb = F.conv2d(actv, w, b)
-        return gb.chunk(2, dim=1)
+        return F.conv2d(actv, w, b)
 
-    def forward(self, x, segmap, leaky=None):
-        gamma, beta = self.gamma_beta(x, segmap)
+    def forward(self, x, segmap, leaky=None, pad=0):
+        """norm(x) * (1 + gamma) + beta [-> leaky_relu] [-> reflection pad]."""
+        gb = self.gamma_beta(x, segmap)
+        if self.pono and x.is_cuda and x.dtype == torch.float32:
+            # PONO + modulation + activation + reflection pad: one fused sm_100a kernel each way
+            return _ops.spade_mod(x, gb, pad=pad, slope=1.0 if leaky is None else leaky)
+        gamma, beta = gb.chunk(2, dim=1)
         out = self.param_free_norm(x) * (1 + gamma) + beta
         if leaky is not None:
             out = F.leaky_relu(out, leaky)
+        if pad:
+            out = F.pad(out, (pad, pad, pad, pad), mode="reflect")
         return out
 
 
@@ -165,6 +172,7 @@ class SPADEResnetBlock(nn.Module):
         self.learned_shortcut = fin != fout
         fmiddle = min(fin, fout)
         self.use_se = use_se
+        self.dilation = dilation
         self.pad = nn.ReflectionPad2d(dilation)
         self.conv_0 = nn.Conv2d(fin, fmiddle, kernel_size=3, padding=0, dilation=dilation)
         self.conv_1 = nn.Conv2d(fmiddle, fout, kernel_size=3, padding=0, dilation=dilation)
@@ -190,8 +198,8 @@ class SPADEResnetBlock(nn.Module):
 
     def forward(self, x, seg):
         x_s = self.conv_s(self.norm_s(x, seg)) if self.learned_shortcut else x
-        dx = self.conv_0(self.pad(self.norm_0(x, seg, leaky=0.2)))
-        dx = self.conv_1(self.pad(self.norm_1(dx, seg, leaky=0.2)))
+        dx = self.conv_0(self.norm_0(x, seg, leaky=0.2, pad=self.dilation))
+        dx = self.conv_1(self.norm_1(dx, seg, leaky=0.2, pad=self.dilation))
         if self.use_se:
             dx = self.se_layar(dx)
         return x_s + dx

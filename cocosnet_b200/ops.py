@@ -122,3 +122,40 @@ def corr_warp_bwd_ds(q16, k16, do16, rscale, v16, out, lse, cv, scale, want_pt):
                                                  dst.data_ptr(), _ptr(pt), b, nq, nk, kd, cv, cvk, nkp, nqp,
                                                  float(scale), _stream()), "cocos_corr_warp_bwd_ds")
     return ds[:, :, :nk], dst[:, :, :nq], (pt[:, :, :nq] if want_pt else None)
+
+
+class _SpadeMod(torch.autograd.Function):
+    """y = reflect_pad(lrelu(PONO(x) * (1 + gamma) + beta)) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, gb, pad, slope, eps):
+        x, gb = x.contiguous(), gb.contiguous()
+        _req(x, torch.float32, "x")
+        _req(gb, torch.float32, "gb")
+        b, c, h, w = x.shape
+        y = torch.empty((b, c, h + 2 * pad, w + 2 * pad), dtype=torch.float32, device=x.device)
+        mean = torch.empty((b, h, w), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        _lib.check(_lib.lib().cocos_spade_mod_fwd(x.data_ptr(), gb.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                                  rstd.data_ptr(), b, c, h, w, pad, float(slope), float(eps),
+                                                  _stream()), "cocos_spade_mod_fwd")
+        ctx.save_for_backward(x, gb, mean, rstd)
+        ctx.pad, ctx.slope = pad, slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gb, mean, rstd = ctx.saved_tensors
+        b, c, h, w = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dgb = torch.empty_like(gb)
+        _lib.check(_lib.lib().cocos_spade_mod_bwd(dy.data_ptr(), x.data_ptr(), gb.data_ptr(), mean.data_ptr(),
+                                                  rstd.data_ptr(), dx.data_ptr(), dgb.data_ptr(), b, c, h, w, ctx.pad,
+                                                  float(ctx.slope), _stream()), "cocos_spade_mod_bwd")
+        return dx, dgb, None, None, None
+
+
+def spade_mod(x, gb, pad=0, slope=1.0, eps=1e-5):
+    """x [B,C,H,W], gb [B,2C,H,W] (gamma ; beta) fp32 CUDA -> [B,C,H+2pad,W+2pad]."""
+    return _SpadeMod.apply(x, gb, int(pad), float(slope), float(eps))

@@ -78,6 +78,7 @@ _BASE = [
     ("--video_like", dict(action="store_true")),
     # --- B200 build only (not in the reference) ---
     ("--corr_precision", dict(type=str, default="fp16", choices=("fp16", "split"))),
+    ("--channels_last", dict(action="store_true")),
 ]
 
 _TRAIN = [

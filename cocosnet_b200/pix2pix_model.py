@@ -148,6 +148,12 @@ class Pix2PixModel(torch.nn.Module):
             input_semantics[:, -3:-2] = glasses
             assert ref_semantics[:, -3:-2].sum().item() == 0
             ref_semantics[:, -3:-2] = glasses_ref
+        if getattr(self.opt, "channels_last", False) and self.use_gpu():
+            cl = torch.channels_last
+            input_semantics = input_semantics.contiguous(memory_format=cl)
+            ref_semantics = ref_semantics.contiguous(memory_format=cl)
+            data["image"] = data["image"].contiguous(memory_format=cl)
+            data["ref"] = data["ref"].contiguous(memory_format=cl)
         return (data["label"], input_semantics, data["image"], data["self_ref"], data["ref"], data["label_ref"],
                 ref_semantics)
 

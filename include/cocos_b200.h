@@ -80,6 +80,18 @@ int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const
                            const float* out, const float* lse, void* ds, void* dst, void* pt, int B, int Nq, int Nk,
                            int Kd, int Cv, int Cvk, int Nkp, int Nqp, float scale, void* stream);
 
+/* Fused PONO + SPADE modulation + LeakyReLU + reflection pad, NCHW fp32:
+ *   y[B,C,H+2p,W+2p] = reflect_pad_p( lrelu_slope( (x - mean_c)/sqrt(var_c + eps) * (1 + gamma) + beta ) )
+ * with per-pixel statistics over channels, unbiased variance (normalization.py:63-68), the
+ * modulation of normalization.py:149, architecture.py:94-95 (slope 0.2; pass 1.0 for the
+ * shortcut's plain SPADE) and the ReflectionPad2d of architecture.py:73-74.  gb = [gamma ; beta]
+ * as [B,2C,H,W].  mean/rstd [B,H,W] are saved for the backward, which returns dx [B,C,H,W] and
+ * dgb [B,2C,H,W] from dy [B,C,H+2p,W+2p]. */
+int cocos_spade_mod_fwd(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
+                        int W, int pad, float slope, float eps, void* stream);
+int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
+                        float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

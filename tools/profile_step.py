@@ -17,8 +17,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=8)
     ap.add_argument("--rows", type=int, default=45)
+    ap.add_argument("--channels_last", action="store_true")
+    ap.add_argument("--no_table", action="store_true")
     args = ap.parse_args()
     opt = bench.make_opt(args.b, gpu=True)
+    opt.channels_last = args.channels_last
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
     trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
@@ -39,6 +42,8 @@ def main():
     torch.cuda.synchronize()
     print("step ms: %.2f  (%.2f img/s at B=%d)  peak mem %.1f GB" % (s.elapsed_time(e) / 3, args.b * 3e3 / s.elapsed_time(e),
                                                               args.b, torch.cuda.max_memory_allocated() / 2 ** 30))
+    if args.no_table:
+        return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step()
