@@ -333,12 +333,17 @@ int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* ou
     return -1;
   }
   {
-    // default: two-warpgroup pipeline; COCOS_K1_VARIANT=1 forces the single-warpgroup kernel
+    // default: 256-key tiles (v3) when Cvp <= 64, else the two-warpgroup 128-key pipeline (v2), else the
+    // single-warpgroup kernel below; COCOS_K1_VARIANT=1|2|3 caps the choice (A/B timing)
     static const int variant = [] {
       const char* e = getenv("COCOS_K1_VARIANT");
-      return e ? atoi(e) : 2;
+      return e ? atoi(e) : 3;
     }();
-    if (variant == 2 && corr == nullptr && Cvp <= 128) {
+    if (variant >= 3 && corr == nullptr && Cvp <= 64) {
+      const int rc3 = corr_warp_fwd3_launch(q, k, vt, out, lse, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale, stream);
+      if (rc3 != 1) return rc3;
+    }
+    if (variant >= 2 && corr == nullptr && Cvp <= 128) {
       const int rc2 = corr_warp_fwd2_launch(q, k, vt, out, lse, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale, stream);
       if (rc2 != 1) return rc2;
     }

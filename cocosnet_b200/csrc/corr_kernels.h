@@ -14,6 +14,10 @@ int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* ou
 int corr_warp_fwd2_launch(const void* q, const void* k, const void* vt, float* out, float* lse, int B, int Nq,
                           int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
 
+// 256-key S tiles (UMMA N=256), P in tensor memory (Cvp <= 64); returns 1 if it does not apply
+int corr_warp_fwd3_launch(const void* q, const void* k, const void* vt, float* out, float* lse, int B, int Nq,
+                          int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
+
 // C[b] (MxN fp32, row-major, ldc) = alpha * A[b] (MxK fp16, K contiguous) * B[b]^T (NxK fp16) (+ C if accumulate)
 int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, int N, int K, int lda, int ldb,
                     int ldc, long long stride_a, long long stride_b, long long stride_c, float alpha,

@@ -10,13 +10,15 @@
 #include "ptx.cuh"
 #include "tmap.h"
 
+#include <stdlib.h>
+
 namespace cocos {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int ATOM_BYTES = 128 * BK * 2;
-constexpr int STAGES = 6;
+constexpr int MAX_STAGES = 6;
 constexpr int NUM_THREADS = 192;
 
 struct GemmParams {
@@ -29,20 +31,23 @@ struct GemmParams {
 };
 
 struct GemmBars {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t acc_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  GemmBars* bars = reinterpret_cast<GemmBars*>(smem_gen + STAGES * 2 * ATOM_BYTES);
+  constexpr int STAGES = (BN == 128) ? 6 : 4;
+  constexpr int STAGE_BYTES = ATOM_BYTES + (BN / 128) * ATOM_BYTES;
+  GemmBars* bars = reinterpret_cast<GemmBars*>(smem_gen + STAGES * STAGE_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, bz = blockIdx.z;
@@ -61,7 +66,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tma_prefetch_desc(&tm_b);
   }
   if (warp == 5) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 128);
+    tmem_alloc(smem_u32(&bars->tmem_base), BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -75,9 +80,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int kc = 0; kc < kc_count; ++kc) {
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
         const uint32_t full = smem_u32(&bars->full[st]);
-        mbar_expect_tx(full, 2 * ATOM_BYTES);
-        tma_load_3d(smem0 + st * 2 * ATOM_BYTES, &tm_a, full, kc * BK, m0, bz);
-        tma_load_3d(smem0 + st * 2 * ATOM_BYTES + ATOM_BYTES, &tm_b, full, kc * BK, n0, bz);
+        mbar_expect_tx(full, STAGE_BYTES);
+        tma_load_3d(smem0 + st * STAGE_BYTES, &tm_a, full, kc * BK, m0, bz);
+        tma_load_3d(smem0 + st * STAGE_BYTES + ATOM_BYTES, &tm_b, full, kc * BK, n0, bz);
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
@@ -91,7 +96,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_wait(smem_u32(&bars->full[st]), ph);
       tc_fence_after();
       if (leader) {
-        const uint32_t a_addr = smem0 + st * 2 * ATOM_BYTES;
+        const uint32_t a_addr = smem0 + st * STAGE_BYTES;
         const uint64_t da = make_desc_k_sw128(a_addr), db = make_desc_k_sw128(a_addr + ATOM_BYTES);
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4)
@@ -111,7 +116,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
                         ((p.stride_c & 3) == 0);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem + lane_sel + c * 32, r);
       tmem_wait_ld();
@@ -149,7 +154,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, BN);
   }
 }
 
@@ -171,14 +176,26 @@ int gemm_f16_launch(const void* a, const void* b, float* c, int batch, int M, in
   const uint64_t sa = batch > 1 ? (uint64_t)stride_a * 2 : (uint64_t)M * lda * 2;
   const uint64_t sb = batch > 1 ? (uint64_t)stride_b * 2 : (uint64_t)N * ldb * 2;
   if ((rc = make_tmap_f16_3d(&tm_a, a, K, M, batch, (uint64_t)lda * 2, sa, BK, BM, 1))) return rc;
+  static const int bn = [] {
+    const char* e = getenv("COCOS_GEMM_BN");
+    return (e && atoi(e) == 128) ? 128 : 256;
+  }();
+  const int BN = (bn == 256 && N > 128) ? 256 : 128;
   if ((rc = make_tmap_f16_3d(&tm_b, b, K, N, batch, (uint64_t)ldb * 2, sb, BK, BN, 1))) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.stride_c = stride_c; p.alpha = alpha; p.accumulate = accumulate; p.bf16 = bf16;
   p.c = c;
-  const int smem_bytes = 1024 + STAGES * 2 * ATOM_BYTES + 256;
-  COCOS_CUDA_CHECK(cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int smem_bytes = 1024 + 196608 + 256;  // 6 x 32 KiB or 4 x 48 KiB
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
-  gemm_f16_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
+  if (BN == 256) {
+    COCOS_CUDA_CHECK(
+        cudaFuncSetAttribute(gemm_f16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    gemm_f16_kernel<256><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
+  } else {
+    COCOS_CUDA_CHECK(
+        cudaFuncSetAttribute(gemm_f16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    gemm_f16_kernel<128><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
+  }
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

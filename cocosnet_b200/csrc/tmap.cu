@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cocos {
@@ -47,9 +48,16 @@ int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d
   cuuint64_t strides[2] = {pitch1, pitch2};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
+  static const int promo = [] {
+    const char* e = getenv("COCOS_TMA_L2PROMO");
+    return e ? atoi(e) : 256;
+  }();
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (dims %llu,%llu,%llu box %u,%u,%u)", (int)r,
               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2);
