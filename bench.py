@@ -24,9 +24,9 @@ PER_GPU_BATCH = 8
 METRIC = "images/sec ADE20k 256x256 train step"
 
 
-def make_opt(batch, gpu):
+def make_opt(batch, gpu, device_index=0):
     from cocosnet_b200.options import TrainOptions
-    argv = FLAGS + ["--batchSize", str(batch), "--gpu_ids", "0" if gpu else "-1", "--name", "bench"]
+    argv = FLAGS + ["--batchSize", str(batch), "--gpu_ids", str(device_index) if gpu else "-1", "--name", "bench"]
     opt = TrainOptions().parse(argv, save=False, verbose=False)
     opt.verbose_networks = False
     opt.allow_random_vgg = True  # models/vgg19_conv.pth is not redistributable: seeded random VGG
@@ -94,13 +94,13 @@ def k1_roofline(torch, batch=8, n=4096, kd=256, cv=3, iters=20):
     q16, k16, vt = ops.pack_rows(q), ops.pack_rows(k), ops.pack_v(v)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
-        ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0)
+        ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0, v32=(v if cv <= 4 else None))
     ts = []
     for _ in range(iters):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0)
+        ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0, v32=(v if cv <= 4 else None))
         e.record()
         torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
@@ -186,8 +186,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    opt = make_opt(PER_GPU_BATCH, gpu=True)
-    opt.gpu_ids = [local_rank]
+    opt = make_opt(PER_GPU_BATCH, gpu=True, device_index=local_rank)
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
     trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())

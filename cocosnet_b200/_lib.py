@@ -17,7 +17,7 @@ SIGNATURES = {
     "cocos_last_error": [],
     "cocos_pack_rows_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
     "cocos_pack_v_f16": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp],
-    "cocos_corr_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+    "cocos_corr_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                             _c_float, _vp],
     "cocos_corr_warp_bwd_ds": [_vp] * 10 + [_c_int] * 8 + [_c_float, _vp],
     "cocos_spade_mod_fwd": [_vp] * 5 + [_c_int] * 5 + [_c_float, _c_float, _vp],

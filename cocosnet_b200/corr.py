@@ -36,8 +36,12 @@ class _Attend(torch.autograd.Function):
         split_q, split_k = (1, 2) if precision == "split" else (0, 0)
         q16 = ops.pack_rows(q.contiguous(), split=split_q)
         k16 = ops.pack_rows(k.contiguous(), split=split_k)
-        vt = ops.pack_v(v.contiguous())
-        out, lse, _ = ops.corr_warp_fwd(q16, k16, vt, v.shape[1], k.shape[2], scale, want_lse=True)
+        v = v.contiguous()
+        if v.shape[1] <= 4 and k.shape[2] % 4 == 0:
+            # <= 4 value channels (the RGB exemplar): fp32 values straight into the CUDA-core-PV kernel
+            out, lse, _ = ops.corr_warp_fwd(q16, k16, None, v.shape[1], k.shape[2], scale, want_lse=True, v32=v)
+        else:
+            out, lse, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(v), v.shape[1], k.shape[2], scale, want_lse=True)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.scale = scale
         ctx.precision = precision

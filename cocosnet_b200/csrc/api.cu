@@ -20,13 +20,14 @@ int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp
   return pack_v_f16_launch(src, dst, B, Cv, Nk, Cvp, Nkp, bf16, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
-                        int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, void* stream) {
-  if (!q || !k || !vt || !out) {
+int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, const float* v32, float* out, float* lse,
+                        float* corr, int B, int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale,
+                        void* stream) {
+  if (!q || !k || (!vt && !v32) || !out) {
     set_error("cocos_corr_warp_fwd: null pointer argument");
     return -1;
   }
-  return corr_warp_fwd_launch(q, k, vt, out, lse, corr, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale,
+  return corr_warp_fwd_launch(q, k, vt, v32, out, lse, corr, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale,
                               static_cast<cudaStream_t>(stream));
 }
 

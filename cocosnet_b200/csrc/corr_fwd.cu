@@ -314,14 +314,28 @@ corr_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
-                         int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream) {
+int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, const float* v32, float* out, float* lse,
+                         float* corr, int B, int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale,
+                         cudaStream_t stream) {
   if (B <= 0 || Nq <= 0 || Nk <= 0) {
     set_error("corr_warp_fwd: empty problem (B=%d Nq=%d Nk=%d)", B, Nq, Nk);
     return -1;
   }
   if (Kd <= 0 || (Kd % BK) != 0) {
     set_error("corr_warp_fwd: Kd=%d must be a positive multiple of 64 (pad in the pack kernel)", Kd);
+    return -1;
+  }
+  static const int variant = [] {
+    // default: best kernel that applies; COCOS_K1_VARIANT=1..4 caps the choice (A/B timing)
+    const char* e = getenv("COCOS_K1_VARIANT");
+    return e ? atoi(e) : 4;
+  }();
+  if (variant >= 4 && v32 != nullptr && corr == nullptr && Cv >= 1 && Cv <= 4) {
+    const int rc4 = corr_warp_fwd4_launch(q, k, v32, out, lse, B, Nq, Nk, Kd, Cv, scale, stream);
+    if (rc4 != 1) return rc4;
+  }
+  if (vt == nullptr) {
+    set_error("corr_warp_fwd: packed fp16 values (vt) are required for this shape (Cv=%d)", Cv);
     return -1;
   }
   if (Cv <= 0 || Cvp < Cv || (Cvp % 16) != 0 || Cvp > 256) {
@@ -333,12 +347,8 @@ int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* ou
     return -1;
   }
   {
-    // default: 256-key tiles (v3) when Cvp <= 64, else the two-warpgroup 128-key pipeline (v2), else the
-    // single-warpgroup kernel below; COCOS_K1_VARIANT=1|2|3 caps the choice (A/B timing)
-    static const int variant = [] {
-      const char* e = getenv("COCOS_K1_VARIANT");
-      return e ? atoi(e) : 3;
-    }();
+    // 256-key tiles (v3) when Cvp <= 64, else the two-warpgroup 128-key pipeline (v2), else the
+    // single-warpgroup kernel below
     if (variant >= 3 && corr == nullptr && Cvp <= 64) {
       const int rc3 = corr_warp_fwd3_launch(q, k, vt, out, lse, B, Nq, Nk, Kd, Cv, Cvp, Nkp, scale, stream);
       if (rc3 != 1) return rc3;

@@ -7,8 +7,14 @@
 
 namespace cocos {
 
-int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
-                         int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, cudaStream_t stream);
+// v32 (optional): the values as fp32 [B, Cv, Nk]; with Cv <= 4 the CUDA-core-PV kernel (corr_fwd4.cu) is used
+int corr_warp_fwd_launch(const void* q, const void* k, const void* vt, const float* v32, float* out, float* lse,
+                         float* corr, int B, int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale,
+                         cudaStream_t stream);
+
+// Cv <= 4: P V on the CUDA cores inside the exp loop, S double buffered at N=256; returns 1 if it does not apply
+int corr_warp_fwd4_launch(const void* q, const void* k, const float* v, float* out, float* lse, int B, int Nq, int Nk,
+                          int Kd, int Cv, float scale, cudaStream_t stream);
 
 // two-softmax-warpgroup variant (Cvp <= 128, no corr dump); returns 1 if it does not apply
 int corr_warp_fwd2_launch(const void* q, const void* k, const void* vt, float* out, float* lse, int B, int Nq,

@@ -29,36 +29,56 @@ __device__ __forceinline__ int reflect(int i, int n) {
   return i;
 }
 
-__global__ void __launch_bounds__(256)
+// Thread mapping: blockDim = (32 pixels, S channel slices).  A warp = 32 consecutive (padded) pixels of one
+// slice, so every global access is a coalesced 128 B row; thread (x, y) walks channels y, y+S, y+2S, ...; the
+// per-pixel sums are reduced across the S slices through shared memory.  S = 8 for wide maps, 32 for the
+// 8x8 .. 32x32 maps with 512-1024 channels (a thread-per-pixel mapping leaves those layers with a few hundred
+// threads on the whole GPU).
+template <int S>
+__device__ __forceinline__ float slice_reduce(float v, float (*red)[32]) {
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < S; ++i) t += red[i][threadIdx.x];
+  __syncthreads();
+  return t;
+}
+
+template <int S>
+__global__ void __launch_bounds__(32 * S)
 spade_mod_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gb, float* __restrict__ y,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int H, int W, int pad,
                      float slope, float eps) {
+  __shared__ float red[S][32];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int b = blockIdx.y;
-  const int op = blockIdx.x * blockDim.x + threadIdx.x;  // padded output pixel
-  if (op >= Hp * Wp) return;
-  const int ho = op / Wp, wo = op - ho * Wp;
+  const int op = blockIdx.x * 32 + threadIdx.x;  // padded output pixel
+  const bool live = op < Hp * Wp;
+  const int opc = live ? op : 0;
+  const int ho = opc / Wp, wo = opc - ho * Wp;
   const int hs = reflect(ho - pad, H), ws = reflect(wo - pad, W);
   const size_t hw = static_cast<size_t>(H) * W;
   const size_t pix = static_cast<size_t>(hs) * W + ws;
   const float* xp = x + static_cast<size_t>(b) * C * hw + pix;
   const float* gp = gb + static_cast<size_t>(b) * 2 * C * hw + pix;
   float sum = 0.f;
-  for (int c = 0; c < C; ++c) sum += xp[c * hw];
-  const float mean = sum / C;
+  for (int c = threadIdx.y; c < C; c += S) sum += xp[c * hw];
+  const float mean = slice_reduce<S>(sum, red) / C;
   float ss = 0.f;
-  for (int c = 0; c < C; ++c) {
+  for (int c = threadIdx.y; c < C; c += S) {
     const float d = xp[c * hw] - mean;
     ss = fmaf(d, d, ss);
   }
-  const float rstd = rsqrtf(ss / (C - 1) + eps);
-  if (ho - pad == hs && wo - pad == ws) {  // interior pixel: owns the saved statistics
+  const float rstd = rsqrtf(slice_reduce<S>(ss, red) / (C - 1) + eps);
+  if (!live) return;
+  if (threadIdx.y == 0 && ho - pad == hs && wo - pad == ws) {  // interior pixel: owns the saved statistics
     mean_out[static_cast<size_t>(b) * hw + pix] = mean;
     rstd_out[static_cast<size_t>(b) * hw + pix] = rstd;
   }
-  float* yp = y + static_cast<size_t>(b) * C * Hp * Wp + op;
   const size_t hwp = static_cast<size_t>(Hp) * Wp;
-  for (int c = 0; c < C; ++c) {
+  float* yp = y + static_cast<size_t>(b) * C * hwp + op;
+  for (int c = threadIdx.y; c < C; c += S) {
     const float xh = (xp[c * hw] - mean) * rstd;
     float z = fmaf(xh, 1.0f + gp[c * hw], gp[(C + c) * hw]);
     z = z > 0.f ? z : z * slope;
@@ -83,15 +103,18 @@ __device__ __forceinline__ float folded_dy(const float* __restrict__ dyc, int h,
   return acc;
 }
 
-__global__ void __launch_bounds__(256)
+template <int S>
+__global__ void __launch_bounds__(32 * S)
 spade_mod_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gb,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dx,
                      float* __restrict__ dgb, int C, int H, int W, int pad, float slope) {
+  __shared__ float red[S][32];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int b = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t hw = static_cast<size_t>(H) * W;
-  if (pix >= static_cast<int>(hw)) return;
+  const int pixi = blockIdx.x * 32 + threadIdx.x;
+  const bool live = pixi < static_cast<int>(hw);
+  const int pix = live ? pixi : 0;
   const int h = pix / W, w = pix - h * W;
   const size_t hwp = static_cast<size_t>(Hp) * Wp;
   const float* xp = x + static_cast<size_t>(b) * C * hw + pix;
@@ -102,21 +125,25 @@ spade_mod_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   const float mean = mean_in[static_cast<size_t>(b) * hw + pix];
   const float rstd = rstd_in[static_cast<size_t>(b) * hw + pix];
   float s1 = 0.f, s2 = 0.f;
-  for (int c = 0; c < C; ++c) {
+  for (int c = threadIdx.y; c < C; c += S) {
     const float xh = (xp[c * hw] - mean) * rstd;
     const float g1 = 1.0f + gp[c * hw];
     const float z = fmaf(xh, g1, gp[(C + c) * hw]);
     float dz = pad ? folded_dy(dyb + c * hwp, h, w, H, W, pad, Wp) : dyb[c * hwp + pix];
     dz = z > 0.f ? dz : dz * slope;
-    dgp[c * hw] = dz * xh;        // d gamma
-    dgp[(C + c) * hw] = dz;       // d beta
     const float dxh = dz * g1;
-    dxp[c * hw] = dxh;            // stash; finished in the second pass
+    if (live) {
+      dgp[c * hw] = dz * xh;   // d gamma
+      dgp[(C + c) * hw] = dz;  // d beta
+      dxp[c * hw] = dxh;       // stash; finished in the second pass (same thread re-reads it)
+    }
     s1 += dxh;
     s2 = fmaf(dxh, xh, s2);
   }
-  const float m1 = s1 / C, m2 = s2 / (C - 1);
-  for (int c = 0; c < C; ++c) {
+  const float m1 = slice_reduce<S>(s1, red) / C;
+  const float m2 = slice_reduce<S>(s2, red) / (C - 1);
+  if (!live) return;
+  for (int c = threadIdx.y; c < C; c += S) {
     const float xh = (xp[c * hw] - mean) * rstd;
     dxp[c * hw] = rstd * (dxp[c * hw] - m1 - xh * m2);
   }
@@ -131,8 +158,11 @@ int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean,
     return -1;
   }
   const int npix = (H + 2 * pad) * (W + 2 * pad);
-  spade_mod_fwd_kernel<<<dim3((npix + 255) / 256, B), 256, 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope,
-                                                                        eps);
+  const dim3 grid((npix + 31) / 32, B);
+  if (C >= 256 && npix <= 64 * 64)
+    spade_mod_fwd_kernel<32><<<grid, dim3(32, 32), 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope, eps);
+  else
+    spade_mod_fwd_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope, eps);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -144,8 +174,11 @@ int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const
     set_error("spade_mod_bwd: bad shape (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
     return -1;
   }
-  spade_mod_bwd_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, stream>>>(dy, x, gb, mean, rstd, dx, dgb, C, H, W,
-                                                                         pad, slope);
+  const dim3 grid((H * W + 31) / 32, B);
+  if (C >= 256 && H * W <= 64 * 64)
+    spade_mod_bwd_kernel<32><<<grid, dim3(32, 32), 0, stream>>>(dy, x, gb, mean, rstd, dx, dgb, C, H, W, pad, slope);
+  else
+    spade_mod_bwd_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(dy, x, gb, mean, rstd, dx, dgb, C, H, W, pad, slope);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

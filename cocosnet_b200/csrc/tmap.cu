@@ -66,4 +66,26 @@ int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d
   return 0;
 }
 
+int make_tmap_f32_3d_plain(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
+                           uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -3;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch1 & 15) || (pitch2 & 15)) {
+    set_error("tensor map (fp32): base/pitches must be 16-byte aligned");
+    return -1;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1, pitch2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(fp32) failed: CUresult %d", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
 }  // namespace cocos

@@ -16,6 +16,10 @@ const char* get_error();
 int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                      uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2);
 
+// fp32 tensor [d2][d1][d0], no swizzle (plain row-major box in shared memory), OOB -> zero fill.
+int make_tmap_f32_3d_plain(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
+                           uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2);
+
 #define COCOS_CUDA_CHECK(expr)                                                            \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

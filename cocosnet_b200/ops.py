@@ -50,19 +50,29 @@ def pack_v(v):
     return out
 
 
-def corr_warp_fwd(q16, k16, vt16, cv, nk, scale, want_lse=True, want_corr=False):
-    """K1 forward.  q16 [B,Nq,Kd], k16 [B,Nk,Kd], vt16 [B,Cvp,Nkp] fp16.
+def corr_warp_fwd(q16, k16, vt16, cv, nk, scale, want_lse=True, want_corr=False, v32=None):
+    """K1 forward.  q16 [B,Nq,Kd], k16 [B,Nk,Kd] fp16; values either packed fp16 vt16 [B,Cvp,Nkp]
+    (pack_v) or, for cv <= 4, the raw fp32 v32 [B,cv,Nk] (vt16 may then be None).
     Returns (out [B,cv,Nq] fp32, lse [B,Nq] | None, corr [B,Nq,Nk] | None)."""
-    for t, nme in ((q16, "q16"), (k16, "k16"), (vt16, "vt16")):
-        _req(t, torch.float16, nme)
+    _req(q16, torch.float16, "q16")
+    _req(k16, torch.float16, "k16")
     b, nq, kd = q16.shape
-    if k16.shape[0] != b or k16.shape[2] != kd or k16.shape[1] != nk or vt16.shape[0] != b:
-        raise _lib.CocosError("corr_warp_fwd: inconsistent shapes %s %s %s" % (q16.shape, k16.shape, vt16.shape))
-    cvp, nkp = vt16.shape[1], vt16.shape[2]
+    if k16.shape[0] != b or k16.shape[2] != kd or k16.shape[1] != nk:
+        raise _lib.CocosError("corr_warp_fwd: inconsistent shapes %s %s" % (q16.shape, k16.shape))
+    cvp = nkp = 0
+    if vt16 is not None:
+        _req(vt16, torch.float16, "vt16")
+        cvp, nkp = vt16.shape[1], vt16.shape[2]
+    if v32 is not None:
+        _req(v32, torch.float32, "v32")
+        if tuple(v32.shape) != (b, cv, nk):
+            raise _lib.CocosError("corr_warp_fwd: v32 must be [B,cv,Nk]")
+    if vt16 is None and (v32 is None or cv > 4 or nk % 4 != 0 or want_corr):
+        raise _lib.CocosError("corr_warp_fwd: packed fp16 values required for this shape")
     out = torch.empty((b, cv, nq), dtype=torch.float32, device=q16.device)
     lse = torch.empty((b, nq), dtype=torch.float32, device=q16.device) if want_lse else None
     corr = torch.empty((b, nq, nk), dtype=torch.float32, device=q16.device) if want_corr else None
-    _lib.check(_lib.lib().cocos_corr_warp_fwd(q16.data_ptr(), k16.data_ptr(), vt16.data_ptr(), out.data_ptr(),
+    _lib.check(_lib.lib().cocos_corr_warp_fwd(q16.data_ptr(), k16.data_ptr(), _ptr(vt16), _ptr(v32), out.data_ptr(),
                                               _ptr(lse), _ptr(corr), b, nq, nk, kd, cv, cvp, nkp, float(scale),
                                               _stream()), "cocos_corr_warp_fwd")
     return out, lse, corr

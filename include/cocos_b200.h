@@ -49,14 +49,17 @@ int cocos_pack_v_f16(const float* src, void* dst, int B, int Cv, int Nk, int Cvp
  *   y = matmul(f_div_C, ref)                correspondence.py:318 (and :334, :343-344,
  *                                           :362, :368, :370 with operands swapped)
  * q  : fp16 [B, Nq, Kd]   k : fp16 [B, Nk, Kd]   (Kd % 64 == 0)
- * vt : fp16 [B, Cvp, Nkp] (values, channel-major)
+ * vt : fp16 [B, Cvp, Nkp] (values, channel-major; cocos_pack_v_f16).  May be NULL when v32 is given and Cv <= 4.
+ * v32: fp32 [B, Cv, Nk] the same values unpacked (may be NULL).  With Cv <= 4 (the avg-pooled RGB exemplar of
+ *      correspondence.py:313-318) the product with the values runs on the CUDA cores inside the exp loop, in fp32.
  * out: fp32 [B, Cv, Nq]   = y.permute(0, 2, 1)  (correspondence.py:323)
  * lse: fp32 [B, Nq] natural-log row log-sum-exp of scale*f (may be NULL)
  * corr: fp32 [B, Nq, Nk] scaled logits f/temperature (may be NULL; the
  *       `return_corr=True` output of correspondence.py:305-306)
  * scale = 1 / temperature. */
-int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, float* out, float* lse, float* corr, int B,
-                        int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale, void* stream);
+int cocos_corr_warp_fwd(const void* q, const void* k, const void* vt, const float* v32, float* out, float* lse,
+                        float* corr, int B, int Nq, int Nk, int Kd, int Cv, int Cvp, int Nkp, float scale,
+                        void* stream);
 
 /* Batched tcgen05 GEMM: C[b] (MxN fp32 row-major, ldc) = alpha * A[b] (MxK fp16,
  * K contiguous, lda) * B[b]^T (NxK fp16, ldb) (+ C[b] if accumulate); `bf16` != 0

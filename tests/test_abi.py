@@ -25,6 +25,6 @@ def test_bad_arguments_are_errors_not_crashes():
         _lib.build()
     h = _lib.lib()
     # argument validation happens before any CUDA call
-    assert h.cocos_corr_warp_fwd(None, None, None, None, None, None, 1, 1, 1, 64, 3, 16, 8, 1.0, None) != 0
+    assert h.cocos_corr_warp_fwd(None, None, None, None, None, None, None, 1, 1, 1, 64, 3, 16, 8, 1.0, None) != 0
     assert b"null" in h.cocos_last_error()
     assert h.cocos_pack_rows_f16(None, None, 0, 1, 1, 2, 0, None, None) != 0

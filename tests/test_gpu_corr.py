@@ -97,6 +97,31 @@ def test_corr_warp_fwd_vs_oracle(b, nq, nk, kd, cv, scale, peaky):
     assert _rel(out.cpu().numpy(), o_true.transpose(0, 2, 1)) < tol
 
 
+V32_CASES = [c for c in FWD_CASES if c[4] <= 4 and c[2] % 4 == 0] + [(2, 300, 520, 128, 1, 100.0, False),
+                                                                        (1, 4096, 4096, 256, 3, 100.0, False),
+                                                                        (1, 256, 100, 64, 4, 100.0, False)]
+
+
+@pytest.mark.parametrize("b,nq,nk,kd,cv,scale,peaky", V32_CASES)
+def test_corr_warp_fwd_fp32_values_kernel(b, nq, nk, kd, cv, scale, peaky):
+    """cv <= 4: the CUDA-core-PV kernel (fp32 P, fp32 V, 256-key double-buffered S tiles)."""
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    q, k, v = _make_qkv(b, nq, nk, kd, cv, peaky)
+    q16 = ops.pack_rows(torch.from_numpy(q).cuda())
+    k16 = ops.pack_rows(torch.from_numpy(k).cuda())
+    out, lse, _ = ops.corr_warp_fwd(q16, k16, None, cv, nk, scale, want_lse=True, v32=torch.from_numpy(v).cuda())
+    qr = q16.float().cpu().numpy()[:, :, :kd]
+    kr = k16.float().cpu().numpy()[:, :, :kd]
+    o_ref, lse_ref = oc.attend(qr, kr, v.transpose(0, 2, 1), scale)
+    # only the MMA's fp32 accumulation order and ex2.approx separate this from the oracle
+    assert _rel(out.cpu().numpy(), o_ref.transpose(0, 2, 1)) < 2e-5
+    assert np.abs(lse.cpu().numpy() - lse_ref).max() < 2e-3
+    o_true, _ = oc.attend(q.transpose(0, 2, 1), k.transpose(0, 2, 1), v.transpose(0, 2, 1), scale)
+    tol = 2e-3 if (peaky or kd < 128) else 1e-3
+    assert _rel(out.cpu().numpy(), o_true.transpose(0, 2, 1)) < tol
+
+
 def test_corr_warp_fwd_split_precision():
     """3-term fp16 split along K: ~1e-5 class error (strict mode)."""
     from cocosnet_b200 import ops
@@ -221,3 +246,37 @@ def test_attend_backward_wide_dynamic_range():
     assert np.median(num / den) < 1e-2 and np.quantile(num / den, 0.99) < 5e-2
     assert _rel(tk.grad.cpu().numpy(), dk.transpose(0, 2, 1)) < 1e-2
     assert _rel(tv.grad.cpu().numpy(), dv.transpose(0, 2, 1)) < 1e-2
+
+
+@pytest.mark.parametrize("b,c,h,w,pad,slope", [(2, 64, 16, 16, 1, 0.2), (1, 1024, 8, 8, 1, 0.2), (2, 130, 20, 12, 0, 1.0),
+                                               (1, 512, 64, 64, 1, 0.2), (1, 96, 33, 17, 2, 0.2)])
+def test_spade_mod_fused_vs_oracle_and_autograd(b, c, h, w, pad, slope):
+    """Fused PONO + SPADE modulation + LeakyReLU + reflection pad (normalization.py:63-68,149;
+    architecture.py:73-74,94-95): forward vs the numpy oracle, backward vs torch autograd of the
+    reference expression (fp64)."""
+    import torch.nn.functional as F
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    rng = np.random.default_rng(c + h)
+    x = rng.standard_normal((b, c, h, w)).astype(np.float32) * 2 + 0.5
+    gb = (rng.standard_normal((b, 2 * c, h, w)) * 0.5).astype(np.float32)
+    tx = torch.from_numpy(x).cuda().requires_grad_(True)
+    tgb = torch.from_numpy(gb).cuda().requires_grad_(True)
+    y = ops.spade_mod(tx, tgb, pad=pad, slope=slope)
+    want = oc.spade_modulate(x, gb[:, :c], gb[:, c:], leaky=slope)
+    if pad:
+        want = np.pad(want, ((0, 0), (0, 0), (pad, pad), (pad, pad)), mode="reflect")
+    assert y.shape == want.shape
+    assert np.abs(y.detach().cpu().numpy() - want).max() < 2e-4
+    dy = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32)).cuda()
+    y.backward(dy)
+    rx = torch.from_numpy(x).double().requires_grad_(True)
+    rgb = torch.from_numpy(gb).double().requires_grad_(True)
+    mean = rx.mean(1, keepdim=True)
+    ref = (rx - mean) / rx.var(1, keepdim=True).add(1e-5).sqrt() * (1 + rgb[:, :c]) + rgb[:, c:]
+    ref = F.leaky_relu(ref, slope)
+    if pad:
+        ref = F.pad(ref, (pad, pad, pad, pad), mode="reflect")
+    ref.backward(dy.double().cpu())
+    assert _rel(tx.grad.cpu().numpy(), rx.grad.numpy()) < 1e-4
+    assert _rel(tgb.grad.cpu().numpy(), rgb.grad.numpy()) < 1e-4

@@ -44,7 +44,7 @@ def main():
         k = k / k.norm(dim=1, keepdim=True)
         v = torch.rand(b, cv, n, device="cuda")
         q16, k16, vt = ops.pack_rows(q), ops.pack_rows(k), ops.pack_v(v)
-        med, best = timeit(lambda: ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0), flush=flush)
+        med, best = timeit(lambda: ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0, v32=(v if cv <= 4 else None)), flush=flush)
         fl = b * (2.0 * n * n * kd + 2.0 * n * n * cv)
         res["k1_fwd_kd%d_cv%d" % (kd, cv)] = dict(ms=med, best_ms=best, tflops=fl / med / 1e9,
                                                  us_per_img=med * 1e3 / b)

@@ -1,6 +1,6 @@
 """A/B the K1 variants inside one process environment each (same box)."""
 import os, subprocess, sys
-for var in (3, 2, 3, 2):
+for var in (4, 3, 4, 3):
     r = subprocess.run([sys.executable, "tools/bench_k1.py"], env=dict(os.environ, COCOS_K1_VARIANT=str(var)), capture_output=True, text=True)
     import json
     try:

@@ -11,11 +11,11 @@ q = torch.randn(b, kd, n, device='cuda'); q = q / q.norm(dim=1, keepdim=True)
 k = torch.randn(b, kd, n, device='cuda'); k = k / k.norm(dim=1, keepdim=True)
 v = torch.rand(b, cv, n, device='cuda')
 q16, k16, vt = ops.pack_rows(q), ops.pack_rows(k), ops.pack_v(v)
-for _ in range(3): ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0)
+for _ in range(3): ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0, v32=(v if cv <= 4 else None))
 ts = []
 for _ in range(10):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(); ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0); e.record(); torch.cuda.synchronize()
+    s.record(); ops.corr_warp_fwd(q16, k16, vt, cv, n, 100.0, v32=(v if cv <= 4 else None)); e.record(); torch.cuda.synchronize()
     ts.append(s.elapsed_time(e))
 ts.sort(); print('%.4f' % ts[len(ts)//2])
 """], env=env, capture_output=True, text=True)

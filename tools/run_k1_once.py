@@ -23,6 +23,6 @@ k = k / k.norm(dim=1, keepdim=True)
 v = torch.rand(a.b, a.cv, a.n, device="cuda")
 q16, k16, vt = ops.pack_rows(q), ops.pack_rows(k), ops.pack_v(v)
 for _ in range(a.reps):
-    out, lse, _ = ops.corr_warp_fwd(q16, k16, vt, a.cv, a.n, 100.0)
+    out, lse, _ = ops.corr_warp_fwd(q16, k16, vt, a.cv, a.n, 100.0, v32=(v if a.cv <= 4 else None))
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))
