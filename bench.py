@@ -157,7 +157,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    profile_mode = bool(os.environ.get("BENCH_PROFILE"))  # under ncu: short run, no e2e / roofline / cpu legs
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if profile_mode:
+        warmup = 1
 
     if args.impl == "reference":
         if rank != 0:
@@ -233,6 +236,9 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = _lib.LAUNCHES - l0
     clocks = sampler.stop() if sampler else None
+    if profile_mode:
+        print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
+        return 0
     step_e2e()
     d2h = 4 * len(trainer.get_latest_losses())
     ms_e2e = timed(step_e2e, args.steps)
