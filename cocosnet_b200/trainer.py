@@ -105,9 +105,17 @@ class Pix2PixTrainer:
 
     def run_generator_one_step(self, data, alpha=1):
         self.optimizer_G.zero_grad(set_to_none=True)
-        g_losses, out = self.pix2pix_model(shard_batch(data), mode="generator", alpha=alpha)
-        g_loss = sum(g_losses.values()).mean()
-        g_loss.backward()
+        # The G step only needs the gradient THROUGH the discriminator, not its weight gradients (the reference
+        # computes and then discards them: optimizer_D.zero_grad() runs before they are ever used).
+        for p in self._d_params:
+            p.requires_grad_(False)
+        try:
+            g_losses, out = self.pix2pix_model(shard_batch(data), mode="generator", alpha=alpha)
+            g_loss = sum(g_losses.values()).mean()
+            g_loss.backward()
+        finally:
+            for p in self._d_params:
+                p.requires_grad_(True)
         allreduce_grads(self._g_params)
         self.optimizer_G.step()
         self.g_losses, self.out = g_losses, out

@@ -149,6 +149,13 @@ def test_properties_full_size():
     ones = torch.ones(b, 3, n, device="cuda")
     out, lse, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(ones), 3, n, 100.0)
     assert float((out - 1).abs().max()) < 2e-3
+    # the fp32-value kernel (Cv <= 4) and the packed-fp16-value tensor-core kernels agree
+    v0 = torch.rand(b, 3, n, device="cuda", generator=g)
+    oa, la, _ = ops.corr_warp_fwd(q16, k16, None, 3, n, 100.0, v32=v0)
+    ob, lb, _ = ops.corr_warp_fwd(q16, k16, ops.pack_v(v0), 3, n, 100.0)
+    assert float((oa - ob).abs().max()) < 2e-3 and float((la - lb).abs().max()) < 1e-3
+    onesa, _, _ = ops.corr_warp_fwd(q16, k16, None, 3, n, 100.0, v32=ones)
+    assert float((onesa - 1).abs().max()) < 1e-5  # fp32 P: rows sum to one to rounding
     # linearity in V
     v1 = torch.rand(b, 3, n, device="cuda", generator=g)
     v2 = torch.rand(b, 3, n, device="cuda", generator=g)

@@ -19,7 +19,9 @@ def main():
     ap.add_argument("--rows", type=int, default=45)
     ap.add_argument("--channels_last", action="store_true")
     ap.add_argument("--no_table", action="store_true")
+    ap.add_argument("--cudnn_benchmark", action="store_true")
     args = ap.parse_args()
+    torch.backends.cudnn.benchmark = args.cudnn_benchmark
     opt = bench.make_opt(args.b, gpu=True)
     opt.channels_last = args.channels_last
     torch.manual_seed(0)
