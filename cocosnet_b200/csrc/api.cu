@@ -54,21 +54,23 @@ int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const
 }
 
 int cocos_spade_mod_fwd(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
-                        int W, int pad, float slope, float eps, void* stream) {
+                        int W, int pad, float slope, float eps, int nhwc, void* stream) {
   if (!x || !gb || !y || !mean || !rstd) {
     set_error("cocos_spade_mod_fwd: null pointer argument");
     return -1;
   }
-  return spade_mod_fwd_launch(x, gb, y, mean, rstd, B, C, H, W, pad, slope, eps, static_cast<cudaStream_t>(stream));
+  return spade_mod_fwd_launch(x, gb, y, mean, rstd, B, C, H, W, pad, slope, eps, nhwc,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
-                        float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, void* stream) {
+                        float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
+                        void* stream) {
   if (!dy || !x || !gb || !mean || !rstd || !dx || !dgb) {
     set_error("cocos_spade_mod_bwd: null pointer argument");
     return -1;
   }
-  return spade_mod_bwd_launch(dy, x, gb, mean, rstd, dx, dgb, B, C, H, W, pad, slope,
+  return spade_mod_bwd_launch(dy, x, gb, mean, rstd, dx, dgb, B, C, H, W, pad, slope, nhwc,
                               static_cast<cudaStream_t>(stream));
 }
 

@@ -39,9 +39,9 @@ int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cv
                       cudaStream_t stream);
 
 int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
-                         int W, int pad, float slope, float eps, cudaStream_t stream);
+                         int W, int pad, float slope, float eps, int nhwc, cudaStream_t stream);
 int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
-                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope,
+                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
                          cudaStream_t stream);
 
 }  // namespace cocos

@@ -149,15 +149,137 @@ spade_mod_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   }
 }
 
+// ------------------------------------------------------------------ NHWC (channels_last) variants
+// One warp per pixel: the channel vector of a pixel is contiguous, lanes stride over it with float4 accesses and
+// the per-pixel sums are warp-shuffle reductions.  C % 4 == 0.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+spade_mod_fwd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gb, float* __restrict__ y,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int H, int W, int pad,
+                          float slope, float eps) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int op = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (op >= Hp * Wp) return;  // whole warp
+  const int ho = op / Wp, wo = op - ho * Wp;
+  const int hs = reflect(ho - pad, H), ws = reflect(wo - pad, W);
+  const size_t spix = (static_cast<size_t>(b) * H + hs) * W + ws;
+  const float4* xp = reinterpret_cast<const float4*>(x + spix * C);
+  const float4* gp = reinterpret_cast<const float4*>(gb + spix * 2 * C);
+  float4* yp = reinterpret_cast<float4*>(y + ((static_cast<size_t>(b) * Hp + ho) * Wp + wo) * C);
+  const int n4 = C >> 2;
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xp[i];
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(sum) / C;
+  float ss = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xp[i];
+    const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (C - 1) + eps);
+  if (lane == 0 && ho - pad == hs && wo - pad == ws) {
+    mean_out[spix] = mean;
+    rstd_out[spix] = rstd;
+  }
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xp[i], g = gp[i], be = gp[n4 + i];
+    float4 z;
+    z.x = fmaf((v.x - mean) * rstd, 1.0f + g.x, be.x);
+    z.y = fmaf((v.y - mean) * rstd, 1.0f + g.y, be.y);
+    z.z = fmaf((v.z - mean) * rstd, 1.0f + g.z, be.z);
+    z.w = fmaf((v.w - mean) * rstd, 1.0f + g.w, be.w);
+    z.x = z.x > 0.f ? z.x : z.x * slope;
+    z.y = z.y > 0.f ? z.y : z.y * slope;
+    z.z = z.z > 0.f ? z.z : z.z * slope;
+    z.w = z.w > 0.f ? z.w : z.w * slope;
+    yp[i] = z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+spade_mod_bwd_nhwc_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gb,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                          float* __restrict__ dx, float* __restrict__ dgb, int C, int H, int W, int pad, float slope) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= H * W) return;
+  const int h = pix / W, w = pix - h * W;
+  const size_t spix = static_cast<size_t>(b) * H * W + pix;
+  const int n4 = C >> 2;
+  const float4* xp = reinterpret_cast<const float4*>(x + spix * C);
+  const float4* gp = reinterpret_cast<const float4*>(gb + spix * 2 * C);
+  float4* dxp = reinterpret_cast<float4*>(dx + spix * C);
+  float4* dgp = reinterpret_cast<float4*>(dgb + spix * 2 * C);
+  // padded positions whose reflection source is (h, w)
+  int hc[3], wc[3], nh = 0, nw = 0;
+  hc[nh++] = h + pad;
+  if (h >= 1 && h <= pad) hc[nh++] = pad - h;
+  if (h <= H - 2 && h >= H - 1 - pad) hc[nh++] = 2 * (H - 1) - h + pad;
+  wc[nw++] = w + pad;
+  if (w >= 1 && w <= pad) wc[nw++] = pad - w;
+  if (w <= W - 2 && w >= W - 1 - pad) wc[nw++] = 2 * (W - 1) - w + pad;
+  const float mean = mean_in[spix], rstd = rstd_in[spix];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < nh; ++a)
+      for (int c = 0; c < nw; ++c) {
+        const float4 t =
+            reinterpret_cast<const float4*>(dy + ((static_cast<size_t>(b) * Hp + hc[a]) * Wp + wc[c]) * C)[i];
+        d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+      }
+    const float4 v = xp[i], g = gp[i], be = gp[n4 + i];
+    float4 xh, dg, dxh;
+    xh.x = (v.x - mean) * rstd; xh.y = (v.y - mean) * rstd; xh.z = (v.z - mean) * rstd; xh.w = (v.w - mean) * rstd;
+    d.x = fmaf(xh.x, 1.0f + g.x, be.x) > 0.f ? d.x : d.x * slope;
+    d.y = fmaf(xh.y, 1.0f + g.y, be.y) > 0.f ? d.y : d.y * slope;
+    d.z = fmaf(xh.z, 1.0f + g.z, be.z) > 0.f ? d.z : d.z * slope;
+    d.w = fmaf(xh.w, 1.0f + g.w, be.w) > 0.f ? d.w : d.w * slope;
+    dg.x = d.x * xh.x; dg.y = d.y * xh.y; dg.z = d.z * xh.z; dg.w = d.w * xh.w;
+    dxh.x = d.x * (1.0f + g.x); dxh.y = d.y * (1.0f + g.y); dxh.z = d.z * (1.0f + g.z); dxh.w = d.w * (1.0f + g.w);
+    dgp[i] = dg;       // d gamma
+    dgp[n4 + i] = d;   // d beta
+    dxp[i] = dxh;      // stash
+    s1 += (dxh.x + dxh.y) + (dxh.z + dxh.w);
+    s2 += (dxh.x * xh.x + dxh.y * xh.y) + (dxh.z * xh.z + dxh.w * xh.w);
+  }
+  const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / (C - 1);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = xp[i];
+    float4 t = dxp[i];
+    t.x = rstd * (t.x - m1 - (v.x - mean) * rstd * m2);
+    t.y = rstd * (t.y - m1 - (v.y - mean) * rstd * m2);
+    t.z = rstd * (t.z - m1 - (v.z - mean) * rstd * m2);
+    t.w = rstd * (t.w - m1 - (v.w - mean) * rstd * m2);
+    dxp[i] = t;
+  }
+}
+
 }  // namespace
 
 int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
-                         int W, int pad, float slope, float eps, cudaStream_t stream) {
-  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0) {
-    set_error("spade_mod_fwd: bad shape (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+                         int W, int pad, float slope, float eps, int nhwc, cudaStream_t stream) {
+  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0 || (nhwc && (C % 4))) {
+    set_error("spade_mod_fwd: bad shape (B=%d C=%d H=%d W=%d pad=%d nhwc=%d)", B, C, H, W, pad, nhwc);
     return -1;
   }
   const int npix = (H + 2 * pad) * (W + 2 * pad);
+  if (nhwc) {
+    spade_mod_fwd_nhwc_kernel<<<dim3((npix + 7) / 8, B), 256, 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope,
+                                                                           eps);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const dim3 grid((npix + 31) / 32, B);
   if (C >= 256 && npix <= 64 * 64)
     spade_mod_fwd_kernel<32><<<grid, dim3(32, 32), 0, stream>>>(x, gb, y, mean, rstd, C, H, W, pad, slope, eps);
@@ -168,11 +290,17 @@ int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean,
 }
 
 int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
-                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope,
+                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
                          cudaStream_t stream) {
-  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0) {
-    set_error("spade_mod_bwd: bad shape (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+  if (B <= 0 || C < 2 || H <= pad || W <= pad || pad < 0 || (nhwc && (C % 4))) {
+    set_error("spade_mod_bwd: bad shape (B=%d C=%d H=%d W=%d pad=%d nhwc=%d)", B, C, H, W, pad, nhwc);
     return -1;
+  }
+  if (nhwc) {
+    spade_mod_bwd_nhwc_kernel<<<dim3((H * W + 7) / 8, B), 256, 0, stream>>>(dy, x, gb, mean, rstd, dx, dgb, C, H, W,
+                                                                            pad, slope);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+    return 0;
   }
   const dim3 grid((H * W + 31) / 32, B);
   if (C >= 256 && H * W <= 64 * 64)

@@ -146,6 +146,8 @@ class SPADE(nn.Module):
         # gamma and beta share their input: one conv with concatenated filters -> gb = [gamma ; beta]
         w = torch.cat((self.mlp_gamma.weight, self.mlp_beta.weight), 0)
         b = torch.cat((self.mlp_gamma.bias, self.mlp_beta.bias), 0)
+        if actv.dim() == 4 and actv.is_contiguous(memory_format=torch.channels_last) and not actv.is_contiguous():
+            w = w.contiguous(memory_format=torch.channels_last)
         return F.conv2d(actv, w, b)
 
     def forward(self, x, segmap, leaky=None, pad=0):

@@ -134,35 +134,43 @@ def corr_warp_bwd_ds(q16, k16, do16, rscale, v16, out, lse, cv, scale, want_pt):
     return ds[:, :, :nk], dst[:, :, :nq], (pt[:, :, :nq] if want_pt else None)
 
 
+def _is_cl(t):
+    """channels_last 4-D tensor (and not simultaneously plain-contiguous)."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
 class _SpadeMod(torch.autograd.Function):
-    """y = reflect_pad(lrelu(PONO(x) * (1 + gamma) + beta)) in one kernel each way."""
+    """y = reflect_pad(lrelu(PONO(x) * (1 + gamma) + beta)) in one kernel each way; NCHW or channels_last."""
 
     @staticmethod
     def forward(ctx, x, gb, pad, slope, eps):
-        x, gb = x.contiguous(), gb.contiguous()
-        _req(x, torch.float32, "x")
-        _req(gb, torch.float32, "gb")
+        nhwc = _is_cl(x) and x.shape[1] % 4 == 0
+        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        x, gb = x.contiguous(memory_format=fmt), gb.contiguous(memory_format=fmt)
+        if x.dtype != torch.float32 or gb.dtype != torch.float32 or not x.is_cuda:
+            raise _lib.CocosError("spade_mod: fp32 CUDA tensors required")
         b, c, h, w = x.shape
-        y = torch.empty((b, c, h + 2 * pad, w + 2 * pad), dtype=torch.float32, device=x.device)
+        y = torch.empty((b, c, h + 2 * pad, w + 2 * pad), dtype=torch.float32, device=x.device, memory_format=fmt)
         mean = torch.empty((b, h, w), dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
         _lib.check(_lib.lib().cocos_spade_mod_fwd(x.data_ptr(), gb.data_ptr(), y.data_ptr(), mean.data_ptr(),
                                                   rstd.data_ptr(), b, c, h, w, pad, float(slope), float(eps),
-                                                  _stream()), "cocos_spade_mod_fwd")
+                                                  int(nhwc), _stream()), "cocos_spade_mod_fwd")
         ctx.save_for_backward(x, gb, mean, rstd)
-        ctx.pad, ctx.slope = pad, slope
+        ctx.pad, ctx.slope, ctx.nhwc = pad, slope, nhwc
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, gb, mean, rstd = ctx.saved_tensors
         b, c, h, w = x.shape
-        dy = dy.contiguous()
-        dx = torch.empty_like(x)
-        dgb = torch.empty_like(gb)
+        fmt = torch.channels_last if ctx.nhwc else torch.contiguous_format
+        dy = dy.contiguous(memory_format=fmt)
+        dx = torch.empty_like(x, memory_format=fmt)
+        dgb = torch.empty_like(gb, memory_format=fmt)
         _lib.check(_lib.lib().cocos_spade_mod_bwd(dy.data_ptr(), x.data_ptr(), gb.data_ptr(), mean.data_ptr(),
                                                   rstd.data_ptr(), dx.data_ptr(), dgb.data_ptr(), b, c, h, w, ctx.pad,
-                                                  float(ctx.slope), _stream()), "cocos_spade_mod_bwd")
+                                                  float(ctx.slope), int(ctx.nhwc), _stream()), "cocos_spade_mod_bwd")
         return dx, dgb, None, None, None
 
 

@@ -89,11 +89,13 @@ int cocos_corr_warp_bwd_ds(const void* q, const void* k, const void* do16, const
  * modulation of normalization.py:149, architecture.py:94-95 (slope 0.2; pass 1.0 for the
  * shortcut's plain SPADE) and the ReflectionPad2d of architecture.py:73-74.  gb = [gamma ; beta]
  * as [B,2C,H,W].  mean/rstd [B,H,W] are saved for the backward, which returns dx [B,C,H,W] and
- * dgb [B,2C,H,W] from dy [B,C,H+2p,W+2p]. */
+ * dgb [B,2C,H,W] from dy [B,C,H+2p,W+2p].  nhwc != 0: every tensor is channels-last ([B,H,W,C] in memory,
+ * C % 4 == 0), one warp per pixel. */
 int cocos_spade_mod_fwd(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
-                        int W, int pad, float slope, float eps, void* stream);
+                        int W, int pad, float slope, float eps, int nhwc, void* stream);
 int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,
-                        float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, void* stream);
+                        float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
+                        void* stream);
 
 #ifdef __cplusplus
 }

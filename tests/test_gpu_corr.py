@@ -255,9 +255,10 @@ def test_attend_backward_wide_dynamic_range():
     assert _rel(tv.grad.cpu().numpy(), dv.transpose(0, 2, 1)) < 1e-2
 
 
-@pytest.mark.parametrize("b,c,h,w,pad,slope", [(2, 64, 16, 16, 1, 0.2), (1, 1024, 8, 8, 1, 0.2), (2, 130, 20, 12, 0, 1.0),
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("b,c,h,w,pad,slope", [(2, 64, 16, 16, 1, 0.2), (1, 1024, 8, 8, 1, 0.2), (2, 132, 20, 12, 0, 1.0),
                                                (1, 512, 64, 64, 1, 0.2), (1, 96, 33, 17, 2, 0.2)])
-def test_spade_mod_fused_vs_oracle_and_autograd(b, c, h, w, pad, slope):
+def test_spade_mod_fused_vs_oracle_and_autograd(b, c, h, w, pad, slope, channels_last):
     """Fused PONO + SPADE modulation + LeakyReLU + reflection pad (normalization.py:63-68,149;
     architecture.py:73-74,94-95): forward vs the numpy oracle, backward vs torch autograd of the
     reference expression (fp64)."""
@@ -267,15 +268,17 @@ def test_spade_mod_fused_vs_oracle_and_autograd(b, c, h, w, pad, slope):
     rng = np.random.default_rng(c + h)
     x = rng.standard_normal((b, c, h, w)).astype(np.float32) * 2 + 0.5
     gb = (rng.standard_normal((b, 2 * c, h, w)) * 0.5).astype(np.float32)
-    tx = torch.from_numpy(x).cuda().requires_grad_(True)
-    tgb = torch.from_numpy(gb).cuda().requires_grad_(True)
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    tx = torch.from_numpy(x).cuda().contiguous(memory_format=fmt).requires_grad_(True)
+    tgb = torch.from_numpy(gb).cuda().contiguous(memory_format=fmt).requires_grad_(True)
     y = ops.spade_mod(tx, tgb, pad=pad, slope=slope)
+    assert y.is_contiguous(memory_format=fmt)
     want = oc.spade_modulate(x, gb[:, :c], gb[:, c:], leaky=slope)
     if pad:
         want = np.pad(want, ((0, 0), (0, 0), (pad, pad), (pad, pad)), mode="reflect")
     assert y.shape == want.shape
     assert np.abs(y.detach().cpu().numpy() - want).max() < 2e-4
-    dy = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32)).cuda()
+    dy = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32)).cuda().contiguous(memory_format=fmt)
     y.backward(dy)
     rx = torch.from_numpy(x).double().requires_grad_(True)
     rgb = torch.from_numpy(gb).double().requires_grad_(True)

@@ -21,8 +21,8 @@ def main():
     ap.add_argument("--no_table", action="store_true")
     ap.add_argument("--cudnn_benchmark", action="store_true")
     args = ap.parse_args()
-    torch.backends.cudnn.benchmark = args.cudnn_benchmark
     opt = bench.make_opt(args.b, gpu=True)
+    opt.no_cudnn_benchmark = not args.cudnn_benchmark
     opt.channels_last = args.channels_last
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
