@@ -120,12 +120,18 @@ def k1_roofline(torch, batch=8, n=4096, kd=256, cv=3, iters=20):
 
 
 def cpu_step_images_per_sec(steps, warmup, budget_s=240.0):
-    """The reference's train step on host cores (CPU port, oracle/torch_port.py), batch 1 per step."""
+    """The reference's train step on host cores (CPU port, oracle/torch_port.py), batch 1 per step.
+    Bounded: stops once `budget_s` is spent; with a single completed step that (cold) step is the sample."""
     import torch
     from cocosnet_b200 import data as cdata
     from cocosnet_b200.trainer import Pix2PixTrainer
     from oracle import torch_port
-    torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    threads = max(1, min(avail, 16))  # the box may report far more CPUs than its quota gives
+    torch.set_num_threads(threads)
     opt = make_opt(1, gpu=False)
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
@@ -138,12 +144,11 @@ def cpu_step_images_per_sec(steps, warmup, budget_s=240.0):
             t0 = time.perf_counter()
             trainer.run_generator_one_step(batch)
             trainer.run_discriminator_one_step(batch)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-            if time.perf_counter() - t_begin + dt > budget_s and len(times) >= 1:
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin + times[-1] > budget_s:
                 break
-    return 1.0 / (sum(times) / len(times)), len(times), torch.get_num_threads()
+    timed = times[warmup:] if len(times) > warmup else times[-1:]
+    return 1.0 / (sum(timed) / len(timed)), len(timed), threads
 
 
 def main():
@@ -165,7 +170,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ips, timed, cores = cpu_step_images_per_sec(args.steps, min(args.warmup, 1))
+        ips, timed, cores = cpu_step_images_per_sec(args.steps, min(args.warmup, 1), budget_s=180.0)
         line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus,
                 "steps": timed, "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / ips,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -249,7 +254,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, timed_n, cores = cpu_step_images_per_sec(2, 1, budget_s=60.0)
+        ips, timed_n, cores = cpu_step_images_per_sec(1, 1, budget_s=45.0)
         cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
                "sample": "%d timed G+D train step(s) at batch 1 on host cores (CPU port of the reference step)" % timed_n}
     if rank == 0:

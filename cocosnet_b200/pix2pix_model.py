@@ -224,8 +224,9 @@ class Pix2PixModel(torch.nn.Module):
         return G_losses, gen
 
     def compute_discriminator_loss(self, input_semantics, real_image, GforD, label=None):
+        # the reference marks the detached fake as requiring grad (pix2pix_model.py:285-286) although nothing
+        # reads that gradient; leaving it off skips a useless input-gradient pass through D.
         fake_image = GforD["fake_image"].detach()
-        fake_image.requires_grad_()
         pred_fake, pred_real, _, _, _ = self.discriminate(input_semantics, fake_image, real_image)
         return {"D_Fake": self.criterionGAN(pred_fake, False, for_discriminator=True) * self.opt.weight_gan,
                 "D_real": self.criterionGAN(pred_real, True, for_discriminator=True) * self.opt.weight_gan}
