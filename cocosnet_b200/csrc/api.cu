@@ -74,4 +74,22 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
                               static_cast<cudaStream_t>(stream));
 }
 
+int cocos_inst_act_fwd(const float* x, float* y, float* mean, float* rstd, int planes, int HW, float slope, float eps,
+                       void* stream) {
+  if (!x || !y || !mean || !rstd) {
+    set_error("cocos_inst_act_fwd: null pointer argument");
+    return -1;
+  }
+  return inst_act_fwd_launch(x, y, mean, rstd, planes, HW, slope, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int planes,
+                       int HW, float slope, void* stream) {
+  if (!dy || !x || !mean || !rstd || !dx) {
+    set_error("cocos_inst_act_bwd: null pointer argument");
+    return -1;
+  }
+  return inst_act_bwd_launch(dy, x, mean, rstd, dx, planes, HW, slope, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -38,6 +38,11 @@ int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int K
 int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16,
                       cudaStream_t stream);
 
+int inst_act_fwd_launch(const float* x, float* y, float* mean, float* rstd, int planes, int HW, float slope, float eps,
+                        cudaStream_t stream);
+int inst_act_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int planes,
+                        int HW, float slope, cudaStream_t stream);
+
 int spade_mod_fwd_launch(const float* x, const float* gb, float* y, float* mean, float* rstd, int B, int C, int H,
                          int W, int pad, float slope, float eps, int nhwc, cudaStream_t stream);
 int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const float* mean, const float* rstd,

@@ -109,6 +109,21 @@ def nonspade_norm(opt, norm_type="instance"):
     return wrap
 
 
+def norm_act(layer, x, slope=None):
+    """leaky_relu(layer(x), slope) for a `nonspade_norm` product (a conv, or Sequential(conv, norm));
+    slope None = no activation.  conv -> InstanceNorm2d(affine=False) -> LeakyReLU runs as the conv plus ONE
+    fused sm_100a kernel (forward and backward) instead of stats / normalise / activation passes."""
+    if isinstance(layer, nn.Sequential) and len(layer) == 2 and isinstance(layer[1], nn.InstanceNorm2d) \
+            and not layer[1].affine and not layer[1].track_running_stats:
+        y = layer[0](x)
+        if y.is_cuda and y.dtype == torch.float32:
+            return _ops.inst_act(y, 1.0 if slope is None else slope, layer[1].eps)
+        y = layer[1](y)
+    else:
+        y = layer(x)
+    return y if slope is None else F.leaky_relu(y, slope)
+
+
 def positional_norm(x, eps=1e-5):
     """PONO: per-pixel normalisation over C, unbiased variance (normalization.py:63-68)."""
     mean = x.mean(dim=1, keepdim=True)

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .blocks import Attention, BaseNetwork, equal_lr, nonspade_norm
+from .blocks import Attention, BaseNetwork, equal_lr, nonspade_norm, norm_act
 
 
 class MultiscaleDiscriminator(BaseNetwork):
@@ -91,7 +91,10 @@ class NLayerDiscriminator(BaseNetwork):
             x = results[-1]
             if name == "model3" and self.use_attn:
                 x = self.attn(x)
-            y = sub(x)
+            if len(sub) == 2 and isinstance(sub[1], nn.LeakyReLU):  # [conv (+ norm), LeakyReLU]
+                y = norm_act(sub[0], x, sub[1].negative_slope)
+            else:
+                y = sub(x)
             if self.opt.D_cam > 0 and name == "model3":
                 gap = F.adaptive_avg_pool2d(y, 1)
                 gap_logit = self.gap_fc(gap.view(y.shape[0], -1))

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .blocks import Attention, BaseNetwork, SPADEResnetBlock, equal_lr, nonspade_norm
+from .blocks import Attention, BaseNetwork, SPADEResnetBlock, equal_lr, nonspade_norm, norm_act
 
 
 class SPADEGenerator(BaseNetwork):
@@ -93,9 +93,11 @@ class AdaptiveFeatureGenerator(BaseNetwork):
                 self.deeper2 = SPADEResnetBlock(4 * nf, 4 * nf, opt)
 
     def forward(self, input, seg):
-        x = self.layer1(input)
-        for layer in (self.layer2, self.layer3, self.layer4, self.layer5):
-            x = layer(self.actvn(x))
+        # layer_{k+1}(actvn(layer_k(.))): the LeakyReLU(0.2) is fused into the norm of the layer that feeds it
+        x = input
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            x = norm_act(layer, x, 0.2)
+        x = norm_act(self.layer5, x, None)
         x = self.head_0(x, seg)
         if self.opt.adaptor_nonlocal:
             x = self.attn(x)

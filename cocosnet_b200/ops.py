@@ -177,3 +177,37 @@ class _SpadeMod(torch.autograd.Function):
 def spade_mod(x, gb, pad=0, slope=1.0, eps=1e-5):
     """x [B,C,H,W], gb [B,2C,H,W] (gamma ; beta) fp32 CUDA -> [B,C,H+2pad,W+2pad]."""
     return _SpadeMod.apply(x, gb, int(pad), float(slope), float(eps))
+
+
+class _InstAct(torch.autograd.Function):
+    """LeakyReLU(InstanceNorm2d(x)) (affine=False, biased variance) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, slope, eps):
+        x = x.contiguous()
+        _req(x, torch.float32, "x")
+        b, c, h, w = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty((b * c,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        _lib.check(_lib.lib().cocos_inst_act_fwd(x.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), b * c,
+                                                 h * w, float(slope), float(eps), _stream()), "cocos_inst_act_fwd")
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        b, c, h, w = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        _lib.check(_lib.lib().cocos_inst_act_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                 dx.data_ptr(), b * c, h * w, float(ctx.slope), _stream()),
+                   "cocos_inst_act_bwd")
+        return dx, None, None
+
+
+def inst_act(x, slope=1.0, eps=1e-5):
+    """x [B,C,H,W] fp32 CUDA -> leaky_relu(instance_norm(x), slope)."""
+    return _InstAct.apply(x, float(slope), float(eps))

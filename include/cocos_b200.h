@@ -97,6 +97,15 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
                         void* stream);
 
+/* Fused InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) over `planes` = B*C contiguous planes of HW fp32
+ * elements (NCHW): the norm/activation pairs of the domain adaptor (generator.py:104-113,141-145) and of the
+ * PatchGAN (discriminator.py:92-115; normalization.py:52-53).  mean/rstd [planes] are saved for the backward,
+ * which returns dx from dy.  slope = 1 is the plain instance norm. */
+int cocos_inst_act_fwd(const float* x, float* y, float* mean, float* rstd, int planes, int HW, float slope, float eps,
+                       void* stream);
+int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int planes,
+                       int HW, float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,3 +290,20 @@ def test_spade_mod_fused_vs_oracle_and_autograd(b, c, h, w, pad, slope, channels
     ref.backward(dy.double().cpu())
     assert _rel(tx.grad.cpu().numpy(), rx.grad.numpy()) < 1e-4
     assert _rel(tgb.grad.cpu().numpy(), rgb.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("b,c,h,w,slope", [(2, 8, 16, 16, 0.2), (1, 3, 31, 30, 0.2), (2, 64, 128, 128, 0.2), (1, 512, 31, 31, 1.0)])
+def test_inst_act_fused_vs_torch(b, c, h, w, slope):
+    """Fused InstanceNorm2d + LeakyReLU (generator.py:141-145, discriminator.py:92-115) vs torch fp64."""
+    import torch.nn.functional as F
+    from cocosnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(c * h)
+    x = (torch.randn(b, c, h, w, device="cuda", generator=g) * 3 + 1).requires_grad_(True)
+    dy = torch.randn(b, c, h, w, device="cuda", generator=g)
+    y = ops.inst_act(x, slope)
+    y.backward(dy)
+    xr = x.detach().double().requires_grad_(True)
+    yr = F.leaky_relu(F.instance_norm(xr, eps=1e-5), slope)
+    yr.backward(dy.double())
+    assert float((y.double() - yr).abs().max()) < 1e-4
+    assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
