@@ -56,16 +56,41 @@ class _Attend(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+class Packed:
+    """fp16 K-major operand [B,N,Kd] produced by the fused prologue (no autograd graph behind it)."""
+
+    def __init__(self, t):
+        self.t = t
+
+
 def attend(q, k, v, scale, precision="fp16"):
-    """q [B,Kd,Nq], k [B,Kd,Nk], v [B,Cv,Nk] fp32 CUDA -> [B,Cv,Nq]."""
+    """q [B,Kd,Nq], k [B,Kd,Nk], v [B,Cv,Nk] fp32 CUDA -> [B,Cv,Nq].  q / k may also be `Packed` operands
+    (inference path): forward only."""
+    if isinstance(q, Packed):
+        v = v.contiguous()
+        nk = k.t.shape[1]
+        if v.shape[1] <= 4 and nk % 4 == 0:
+            return ops.corr_warp_fwd(q.t, k.t, None, v.shape[1], nk, scale, want_lse=False, v32=v)[0]
+        return ops.corr_warp_fwd(q.t, k.t, ops.pack_v(v), v.shape[1], nk, scale, want_lse=False)[0]
     return _Attend.apply(q, k, v, float(scale), precision)
 
 
 def raw_correlation(q, k, scale):
     """`return_corr=True` path (correspondence.py:305-306): scaled logits [B,Nq,Nk]."""
-    q16 = ops.pack_rows(q.contiguous())
-    k16 = ops.pack_rows(k.contiguous())
+    q16 = q.t if isinstance(q, Packed) else ops.pack_rows(q.contiguous())
+    k16 = k.t if isinstance(k, Packed) else ops.pack_rows(k.contiguous())
     return ops.gemm_f16(q16, k16, alpha=scale)
+
+
+def _operands(x, match_kernel, pono_c, precision):
+    """theta / phi conv output -> normalised correlation operand.  Without autograd (inference) and with
+    --PONO_C the whole prologue (unfold, centre, normalise, fp16 pack) is one fused kernel pair."""
+    fused = (not (torch.is_grad_enabled() and x.requires_grad)) and pono_c and precision == "fp16" \
+        and match_kernel in (1, 3) and x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0 \
+        and (x.shape[1] * match_kernel * match_kernel) % 64 == 0
+    if fused:
+        return Packed(ops.normalize_pack(x, match_kernel, _EPS))
+    return _unfold_center_normalize(x, match_kernel, pono_c)
 
 
 def correspondence_tail(theta_conv, phi_conv, ref_img, *, match_kernel=3, pono_c=True, temperature=0.01, down=4,
@@ -76,8 +101,11 @@ def correspondence_tail(theta_conv, phi_conv, ref_img, *, match_kernel=3, pono_c
     [B,3,h,w] (or folded [B,3,256,256] for warp_patch); extras holds
     warp_mask / warp_cycle / warp_i2r / warp_i2r2i when requested."""
     b, _, fh, fw = theta_conv.shape
-    theta = _unfold_center_normalize(theta_conv, match_kernel, pono_c)
-    phi = _unfold_center_normalize(phi_conv, match_kernel, pono_c)
+    theta = _operands(theta_conv, match_kernel, pono_c, precision)
+    phi = _operands(phi_conv, match_kernel, pono_c, precision)
+    if isinstance(theta, Packed) != isinstance(phi, Packed):  # keep the two operands in the same K order
+        theta = _unfold_center_normalize(theta_conv, match_kernel, pono_c)
+        phi = _unfold_center_normalize(phi_conv, match_kernel, pono_c)
     scale = 1.0 / temperature
     if return_corr:
         return raw_correlation(theta, phi, scale), {}

@@ -92,4 +92,13 @@ int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const
   return inst_act_bwd_launch(dy, x, mean, rstd, dx, planes, HW, slope, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int match_kernel,
+                         float eps, void* stream) {
+  if (!x || !xt_workspace || !out) {
+    set_error("cocos_normalize_pack: null pointer argument");
+    return -1;
+  }
+  return norm_pack_launch(x, xt_workspace, out, B, C, h, w, match_kernel, eps, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -38,6 +38,9 @@ int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int K
 int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16,
                       cudaStream_t stream);
 
+int norm_pack_launch(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int mk, float eps,
+                     cudaStream_t stream);
+
 int inst_act_fwd_launch(const float* x, float* y, float* mean, float* rstd, int planes, int HW, float slope, float eps,
                         cudaStream_t stream);
 int inst_act_bwd_launch(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int planes,

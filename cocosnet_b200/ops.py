@@ -211,3 +211,16 @@ class _InstAct(torch.autograd.Function):
 def inst_act(x, slope=1.0, eps=1e-5):
     """x [B,C,H,W] fp32 CUDA -> leaky_relu(instance_norm(x), slope)."""
     return _InstAct.apply(x, float(slope), float(eps))
+
+
+def normalize_pack(x, match_kernel, eps):
+    """x [B,C,h,w] fp32 CUDA -> fp16 [B, h*w, C*mk*mk]: unfold + centre over K (--PONO_C) + L2-normalise + pack,
+    fused (no autograd: used on the inference / no-grad path)."""
+    x = x.contiguous()
+    _req(x, torch.float32, "x")
+    b, c, h, w = x.shape
+    out = torch.empty((b, h * w, c * match_kernel * match_kernel), dtype=torch.float16, device=x.device)
+    ws = torch.empty((b, h * w, c), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().cocos_normalize_pack(x.data_ptr(), ws.data_ptr(), out.data_ptr(), b, c, h, w, match_kernel,
+                                               float(eps), _stream()), "cocos_normalize_pack", kernels=2)
+    return out

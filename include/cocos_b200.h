@@ -97,6 +97,13 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
                         void* stream);
 
+/* Fused operand prologue for `--PONO_C` (correspondence.py:273-281 / 283-289): x fp32 [B,C,h,w] (output of the theta
+ * or phi 1x1 conv) -> unfold(match_kernel, zero pad) -> minus the mean over K = C*mk*mk -> / (L2 norm over K + eps)
+ * -> fp16 [B, h*w, K], K laid out tap-major (k = tap*C + c; use the same call for both operands).  xt_workspace:
+ * fp32 scratch of B*C*h*w elements.  match_kernel in {1, 3}; C % 4 == 0; K % 64 == 0. */
+int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int match_kernel,
+                         float eps, void* stream);
+
 /* Fused InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) over `planes` = B*C contiguous planes of HW fp32
  * elements (NCHW): the norm/activation pairs of the domain adaptor (generator.py:104-113,141-145) and of the
  * PatchGAN (discriminator.py:92-115; normalization.py:52-53).  mean/rstd [planes] are saved for the backward,

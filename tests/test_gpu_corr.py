@@ -307,3 +307,32 @@ def test_inst_act_fused_vs_torch(b, c, h, w, slope):
     yr.backward(dy.double())
     assert float((y.double() - yr).abs().max()) < 1e-4
     assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("mk", [1, 3])
+def test_normalize_pack_fused_vs_oracle(mk):
+    """Fused unfold + centre (PONO_C) + normalise + fp16 pack (correspondence.py:273-289) vs the oracle; the
+    K axis is tap-major, so compare through the Gram matrix and the per-position norms."""
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    rng = np.random.default_rng(mk)
+    x = rng.standard_normal((2, 64, 12, 20)).astype(np.float32) + 0.3
+    out = ops.normalize_pack(torch.from_numpy(x).cuda(), mk, 2.220446049250313e-16).float().cpu().numpy()  # [B,N,K]
+    f = oc.unfold(x, mk, padding=mk // 2) if mk > 1 else x.reshape(2, 64, -1)
+    want = oc.center_normalize(f, True)  # [B,K,N], K order c*mk*mk + tap
+    k = 64 * mk * mk
+    want_tm = want.reshape(2, 64, mk * mk, -1).transpose(0, 3, 2, 1).reshape(2, -1, k)  # -> [B,N,tap*C + c]
+    assert out.shape == want_tm.shape
+    assert np.abs(out - want_tm).max() < 1e-3 * np.abs(want_tm).max() + 1e-4  # fp16 rounding of unit vectors
+
+
+def test_tail_inference_path_uses_fused_prologue_and_matches_golden():
+    from cocosnet_b200 import corr
+    from tests.golden import cases
+    import torch.nn.functional as F
+    gold = np.load(os.path.join(GOLD, "tail_ade20k_mk3.npz"))
+    inp = {k: torch.from_numpy(v).cuda() for k, v in cases.tail_inputs("ade20k_mk3").items()}
+    with torch.no_grad():
+        y, _ = corr.correspondence_tail(inp["theta"], inp["phi"], inp["ref_img"], match_kernel=3, pono_c=True)
+        y = F.interpolate(y, scale_factor=4)
+    assert _rel(y.cpu().numpy(), gold["warp_out"].astype(np.float64)) < 1e-3
