@@ -18,6 +18,11 @@ CONFIGS = {
     "ade20k_train": ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
                      "--warp_mask_losstype", "direct", "--weight_mask", "100.0", "--vgg_normal_correct",
                      "--batchSize", "1"],
+    # BASELINE.json configs[2] flags (no --PONO: SPADE's param-free norm is the (Sync)BatchNorm stub) + the cycle term
+    "celebahq_train": ["--dataset_mode", "celebahq", "--warp_bilinear", "--adaptor_kernel", "4",
+                       "--warp_cycle_w", "1.0", "--batchSize", "1"],
+    # BASELINE.json configs[3] flags: 4x4 patch warp + fold, float pose maps
+    "deepfashion_train": ["--dataset_mode", "deepfashion", "--warp_patch", "--video_like", "--batchSize", "1"],
 }
 
 
@@ -37,16 +42,25 @@ def run(name):
         torch.manual_seed(0)
         model = Pix2PixModel(opt)
         model.train()
-        data = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
-        data["label"] = data["label"].long()
-        data["label_ref"] = data["label_ref"].long()  # reference CPU path never casts it (pix2pix_model.py:171-173)
+        def fresh():
+            d = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+            if opt.dataset_mode not in ("deepfashion",):
+                d["label"] = d["label"].long()
+                d["label_ref"] = d["label_ref"].long()  # reference CPU path never casts it (pix2pix_model.py:171-173)
+            return d
+        real_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self  # deepfashion / celebahqedge call .cuda() unconditionally
+        data = fresh()
         g_losses, out = model(data, mode="generator")
         g_loss = sum(g_losses.values()).mean()
         g_loss.backward()
         res = {"g_" + k: v.detach().numpy().astype(np.float64).reshape(-1) for k, v in g_losses.items()}
         res["fake_image_sub"] = out["fake_image"].detach().numpy()[:, :, ::4, ::4]
         res["warp_out_sub"] = out["warp_out"].detach().numpy()[:, :, ::4, ::4]
-        res["warp_mask_chsum"] = out["warp_mask"].detach().numpy().sum(1)
+        if out.get("warp_mask") is not None:
+            res["warp_mask_chsum"] = out["warp_mask"].detach().numpy().sum(1)
+        if out.get("warp_cycle") is not None:
+            res["warp_cycle"] = out["warp_cycle"].detach().numpy()
         gn = {}
         for key in ("netG", "netCorr"):
             for pname, p in model.net[key].named_parameters():
@@ -55,10 +69,8 @@ def run(name):
                                            or pname.endswith("fc.weight") or pname.endswith("attn.gamma")):
                     gn["gradnorm_%s_%s" % (key, pname)] = np.array([float(p.grad.norm())])
         res.update(gn)
-        data2 = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
-        data2["label"] = data2["label"].long()
-        data2["label_ref"] = data2["label_ref"].long()
-        d_losses = model(data2, mode="discriminator", GforD={"fake_image": out["fake_image"]})
+        d_losses = model(fresh(), mode="discriminator", GforD={"fake_image": out["fake_image"]})
+        torch.Tensor.cuda = real_cuda
         res.update({"d_" + k: v.detach().numpy().astype(np.float64).reshape(-1) for k, v in d_losses.items()})
     path = os.path.join(HERE, "model_%s.npz" % name)
     np.savez_compressed(path, **res)

@@ -46,11 +46,21 @@ def test_state_dict_keys_match_reference_snapshot():
         assert mine == snap[name], name
 
 
-@pytest.mark.timeout(600)
-def test_full_train_step_matches_reference_golden():
+MODEL_CONFIGS = {
+    "ade20k_train": ADE_TRAIN,
+    "celebahq_train": ["--dataset_mode", "celebahq", "--warp_bilinear", "--adaptor_kernel", "4", "--warp_cycle_w", "1.0",
+                       "--batchSize", "1", "--gpu_ids", "-1"],
+    "deepfashion_train": ["--dataset_mode", "deepfashion", "--warp_patch", "--video_like", "--batchSize", "1",
+                          "--gpu_ids", "-1"],
+}
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("config", list(MODEL_CONFIGS))
+def test_full_train_step_matches_reference_golden(config):
     from cocosnet_b200.pix2pix_model import Pix2PixModel
-    gold = np.load(os.path.join(GOLD, "model_ade20k_train.npz"))
-    opt = TrainOptions().parse(ADE_TRAIN, save=False, verbose=False)
+    gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
+    opt = TrainOptions().parse(MODEL_CONFIGS[config], save=False, verbose=False)
     opt.verbose_networks = False
     opt.allow_random_vgg = True
     torch.manual_seed(0)
@@ -69,7 +79,10 @@ def test_full_train_step_matches_reference_golden():
         assert np.allclose(v.detach().numpy().reshape(-1), gold["d_" + k], rtol=2e-4), k
     assert np.allclose(out["fake_image"].detach().numpy()[:, :, ::4, ::4], gold["fake_image_sub"], atol=2e-5)
     assert np.allclose(out["warp_out"].detach().numpy()[:, :, ::4, ::4], gold["warp_out_sub"], atol=2e-5)
-    assert np.allclose(out["warp_mask"].detach().numpy().sum(1), gold["warp_mask_chsum"], atol=1e-4)
+    if "warp_mask_chsum" in gold.files:
+        assert np.allclose(out["warp_mask"].detach().numpy().sum(1), gold["warp_mask_chsum"], atol=1e-4)
+    if "warp_cycle" in gold.files:
+        assert np.allclose(out["warp_cycle"].detach().numpy(), gold["warp_cycle"], atol=2e-5)
     for key in gold.files:
         if key.startswith("gradnorm_"):
             _, netk, pname = key.split("_", 2)
