@@ -16,6 +16,10 @@ const char* get_error();
 int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                      uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2);
 
+// fp16 tensor [d3][d2][d1][d0] (d0 contiguous), pitches in BYTES, box (b0,b1,b2,b3), 128B swizzle, OOB -> zero.
+int make_tmap_f16_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t pitches[3],
+                     const uint32_t box[4]);
+
 // fp32 tensor [d2][d1][d0], no swizzle (plain row-major box in shared memory), OOB -> zero fill.
 int make_tmap_f32_3d_plain(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                            uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2);

@@ -224,3 +224,56 @@ def normalize_pack(x, match_kernel, eps):
     _lib.check(_lib.lib().cocos_normalize_pack(x.data_ptr(), ws.data_ptr(), out.data_ptr(), b, c, h, w, match_kernel,
                                                float(eps), _stream()), "cocos_normalize_pack", kernels=2)
     return out
+
+
+def pack_conv_weight(weight):
+    """[Cout, Cin, KS, KS] fp32 -> fp16 [Cout, KS*KS*Cp] with k = (r*KS + s)*Cp + c, Cp = Cin padded to 64."""
+    cout, cin, ks, _ = weight.shape
+    cp = round_up(cin, 64)
+    w = weight.permute(0, 2, 3, 1)
+    if cp != cin:
+        w = torch.nn.functional.pad(w, (0, cp - cin))
+    return w.reshape(cout, ks * ks * cp).to(torch.float16).contiguous()
+
+
+def conv_fwd_native(x, weight, bias, pre_padded):
+    """K2 forward.  x fp32 NCHW [B,Cin,Hin,Win] (pre_padded: Hin = H + KS - 1), weight [Cout,Cin,KS,KS] -> y fp32
+    NCHW [B,Cout,H,W] on the tcgen05 implicit-GEMM kernel (fp16 operands, fp32 accumulate)."""
+    x = x.contiguous()
+    _req(x, torch.float32, "x")
+    b, cin, hin, win = x.shape
+    cout, _, ks, _ = weight.shape
+    h, w = (hin - ks + 1, win - ks + 1) if pre_padded else (hin, win)
+    cp = round_up(cin, 64)
+    x16 = pack_rows(x.view(b, cin, hin * win), kp=cp)  # == NHWC fp16 [B, Hin, Win, Cp]
+    wt = pack_conv_weight(weight)
+    y = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
+    bias_c = None if bias is None else bias.contiguous()
+    _lib.check(_lib.lib().cocos_conv_fwd(x16.data_ptr(), wt.data_ptr(), _ptr(bias_c), y.data_ptr(), b, h, w, cp, cout, ks,
+                                         int(bool(pre_padded)), _stream()), "cocos_conv_fwd")
+    return y
+
+
+class _ConvNative(torch.autograd.Function):
+    """conv2d (stride 1, KS in {1,3}) with the forward on the tcgen05 kernel; the backward (dgrad / wgrad) still goes
+    through aten.convolution_backward (cuDNN) -- K2 backward kernels are the next step."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pre_padded):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.pad = 0 if pre_padded else weight.shape[2] // 2
+        return conv_fwd_native(x, weight, bias, pre_padded)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
+        cout = weight.shape[0]
+        dx, dw, db = torch.ops.aten.convolution_backward(dy.contiguous(), x, weight, [cout] if ctx.has_bias else None,
+                                                         [1, 1], [ctx.pad, ctx.pad], [1, 1], False, [0, 0], 1, mask)
+        return dx, dw, db, None
+
+
+def conv_native(x, weight, bias=None, pre_padded=True):
+    return _ConvNative.apply(x, weight, bias, bool(pre_padded))

@@ -97,6 +97,14 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
                         float* dx, float* dgb, int B, int C, int H, int W, int pad, float slope, int nhwc,
                         void* stream);
 
+/* K2: TMA-fed tcgen05 implicit-GEMM convolution, forward, KS in {1, 3}, stride 1 (the 3x3 convs of the SPADE blocks,
+ * domain adaptor and residual blocks: architecture.py:31-33,73-74; normalization.py:112-120; correspondence.py:17-22).
+ * x  : fp16 NHWC [B, Hin, Win, Cp], Cp % 64 == 0 (cocos_pack_rows_f16 of the NCHW activation viewed as [B,C,Hin*Win]).
+ *      pre_padded != 0: Hin = H + KS - 1, the (reflection) halo is already in x; else Hin = H and the halo is zero.
+ * wt : fp16 [Cout, KS*KS*Cp], k = (r*KS + s)*Cp + c.   bias: fp32 [Cout] or NULL.   y: fp32 NCHW [B, Cout, H, W]. */
+int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Cp, int Cout,
+                   int KS, int pre_padded, void* stream);
+
 /* Fused operand prologue for `--PONO_C` (correspondence.py:273-281 / 283-289): x fp32 [B,C,h,w] (output of the theta
  * or phi 1x1 conv) -> unfold(match_kernel, zero pad) -> minus the mean over K = C*mk*mk -> / (L2 norm over K + eps)
  * -> fp16 [B, h*w, K], K laid out tap-major (k = tap*C + c; use the same call for both operands).  xt_workspace:

@@ -336,3 +336,42 @@ def test_tail_inference_path_uses_fused_prologue_and_matches_golden():
         y, _ = corr.correspondence_tail(inp["theta"], inp["phi"], inp["ref_img"], match_kernel=3, pono_c=True)
         y = F.interpolate(y, scale_factor=4)
     assert _rel(y.cpu().numpy(), gold["warp_out"].astype(np.float64)) < 1e-3
+
+
+CONV_CASES = [
+    # b, cin, cout, h, w, ks, pre_padded
+    (2, 64, 128, 16, 16, 3, True),
+    (1, 154, 128, 32, 32, 3, True),     # SPADE mlp_shared on the one-hot map (Cin padded 154 -> 192)
+    (2, 128, 1024, 8, 8, 3, True),      # gamma/beta conv at the 8x8 stage (N = 256 tiles, half-empty M tile)
+    (1, 64, 64, 256, 256, 3, True),     # up_3 resolution
+    (2, 256, 32, 20, 12, 1, False),     # 1x1, ragged patch
+    (2, 96, 200, 20, 12, 3, False),     # zero padding by TMA out-of-bounds fill, ragged everything
+    (1, 512, 512, 64, 64, 3, False),
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", CONV_CASES)
+def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_padded):
+    """K2 forward (tcgen05 implicit GEMM, fp16 operands) vs torch conv2d in fp64; backward through cuDNN."""
+    import torch.nn.functional as F
+    from cocosnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(cin + h)
+    x = torch.randn(b, cin, h, w, device="cuda", generator=g)
+    wgt = (torch.randn(cout, cin, ks, ks, device="cuda", generator=g) / (cin * ks * ks) ** 0.5).requires_grad_(True)
+    bias = torch.randn(cout, device="cuda", generator=g).requires_grad_(True)
+    pad = ks // 2
+    xin = F.pad(x, (pad, pad, pad, pad), mode="reflect") if (pre_padded and pad) else x
+    xin = xin.clone().requires_grad_(True)
+    y = ops.conv_native(xin, wgt, bias, pre_padded=pre_padded)
+    ref = F.conv2d(xin.detach().double(), wgt.detach().double(), bias.detach().double(), padding=0 if pre_padded else pad)
+    assert y.shape == ref.shape
+    assert _rel(y.detach().cpu().numpy(), ref.cpu().numpy()) < 1e-3
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy)
+    xr = xin.detach().clone().requires_grad_(True)
+    wr = wgt.detach().clone().requires_grad_(True)
+    br = bias.detach().clone().requires_grad_(True)
+    F.conv2d(xr, wr, br, padding=0 if pre_padded else pad).backward(dy)
+    assert _rel(xin.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-3
+    assert _rel(wgt.grad.cpu().numpy(), wr.grad.cpu().numpy()) < 2e-3
+    assert _rel(bias.grad.cpu().numpy(), br.grad.cpu().numpy()) < 1e-4
