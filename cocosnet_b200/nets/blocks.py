@@ -1,8 +1,10 @@
 """Building blocks of the SPADE generator / domain adaptors / PatchGAN
 (host-side mirror; parameter names and shapes match the reference so its
 checkpoints load: reference models/networks/normalization.py,
-architecture.py).  The attention matrix product runs on the fused sm_100a
-kernel; convolutions are still dispatched through torch (cuDNN) in this round.
+architecture.py).  The attention matrix product, the SPADE modulation, the
+instance-norm/activation pairs and the FORWARD of every stride-1 3x3 / 1x1
+convolution run on hand-written sm_100a kernels; conv backward (dgrad/wgrad) and
+the strided 4x4 convolutions still go through cuDNN.
 """
 import re
 
@@ -13,6 +15,20 @@ from torch.nn.utils import spectral_norm
 
 from .. import corr as _corr
 from .. import ops as _ops
+
+
+def conv_apply(conv, x):
+    """`conv(x)` for an nn.Conv2d (possibly wrapped by spectral_norm / equal_lr): stride-1 3x3 / 1x1 convolutions
+    run their forward on the tcgen05 implicit-GEMM kernel (K2, fp16 operands / fp32 accumulate, TF32-class
+    precision); anything else, or `COCOS_NATIVE_CONV=0`, falls back to the module (cuDNN)."""
+    if (_ops.NATIVE_CONV and isinstance(conv, nn.Conv2d) and x.is_cuda and x.dtype == torch.float32
+            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.kernel_size in ((3, 3), (1, 1)) and conv.padding_mode == "zeros"
+            and conv.padding in ((0, 0), (conv.kernel_size[0] // 2,) * 2) and conv.out_channels >= 16):
+        for hook in conv._forward_pre_hooks.values():  # spectral norm / equal-lr materialise conv.weight here
+            hook(conv, (x,))
+        return _ops.conv_native(x, conv.weight, conv.bias, pre_padded=(conv.padding == (0, 0)))
+    return conv(x)
 
 
 class BaseNetwork(nn.Module):
@@ -115,12 +131,12 @@ def norm_act(layer, x, slope=None):
     fused sm_100a kernel (forward and backward) instead of stats / normalise / activation passes."""
     if isinstance(layer, nn.Sequential) and len(layer) == 2 and isinstance(layer[1], nn.InstanceNorm2d) \
             and not layer[1].affine and not layer[1].track_running_stats:
-        y = layer[0](x)
+        y = conv_apply(layer[0], x)
         if y.is_cuda and y.dtype == torch.float32:
             return _ops.inst_act(y, 1.0 if slope is None else slope, layer[1].eps)
         y = layer[1](y)
     else:
-        y = layer(x)
+        y = conv_apply(layer, x) if isinstance(layer, nn.Conv2d) else layer(x)
     return y if slope is None else F.leaky_relu(y, slope)
 
 
@@ -157,12 +173,14 @@ class SPADE(nn.Module):
 
     def gamma_beta(self, x, segmap):
         segmap = F.interpolate(segmap, size=x.size()[2:], mode="nearest")
-        actv = self.pad(self.mlp_shared(segmap))
+        actv = self.pad(F.relu(conv_apply(self.mlp_shared[1], self.mlp_shared[0](segmap))))
         # gamma and beta share their input: one conv with concatenated filters -> gb = [gamma ; beta]
         w = torch.cat((self.mlp_gamma.weight, self.mlp_beta.weight), 0)
         b = torch.cat((self.mlp_gamma.bias, self.mlp_beta.bias), 0)
         if actv.dim() == 4 and actv.is_contiguous(memory_format=torch.channels_last) and not actv.is_contiguous():
-            w = w.contiguous(memory_format=torch.channels_last)
+            return F.conv2d(actv, w.contiguous(memory_format=torch.channels_last), b)
+        if _ops.NATIVE_CONV and actv.is_cuda and actv.dtype == torch.float32 and w.shape[2] in (1, 3):
+            return _ops.conv_native(actv, w, b, pre_padded=True)
         return F.conv2d(actv, w, b)
 
     def forward(self, x, segmap, leaky=None, pad=0):
@@ -214,9 +232,9 @@ class SPADEResnetBlock(nn.Module):
             self.se_layar = SELayer(fout)
 
     def forward(self, x, seg):
-        x_s = self.conv_s(self.norm_s(x, seg)) if self.learned_shortcut else x
-        dx = self.conv_0(self.norm_0(x, seg, leaky=0.2, pad=self.dilation))
-        dx = self.conv_1(self.norm_1(dx, seg, leaky=0.2, pad=self.dilation))
+        x_s = conv_apply(self.conv_s, self.norm_s(x, seg)) if self.learned_shortcut else x
+        dx = conv_apply(self.conv_0, self.norm_0(x, seg, leaky=0.2, pad=self.dilation))
+        dx = conv_apply(self.conv_1, self.norm_1(dx, seg, leaky=0.2, pad=self.dilation))
         if self.use_se:
             dx = self.se_layar(dx)
         return x_s + dx
@@ -255,8 +273,8 @@ class Attention(nn.Module):
 
     def forward(self, x, y=None):
         b, _, h, w = x.shape
-        theta = self.theta(x).reshape(b, self.ch // 8, h * w)
-        phi = F.max_pool2d(self.phi(x), [2, 2]).reshape(b, self.ch // 8, h * w // 4)
-        g = F.max_pool2d(self.g(x), [2, 2]).reshape(b, self.ch // 2, h * w // 4)
+        theta = conv_apply(self.theta, x).reshape(b, self.ch // 8, h * w)
+        phi = F.max_pool2d(conv_apply(self.phi, x), [2, 2]).reshape(b, self.ch // 8, h * w // 4)
+        g = F.max_pool2d(conv_apply(self.g, x), [2, 2]).reshape(b, self.ch // 2, h * w // 4)
         o = _corr.attend(theta, phi, g, 1.0)  # == bmm(g, softmax(bmm(theta^T, phi))^T)
-        return self.gamma * self.o(o.reshape(b, self.ch // 2, h, w)) + x
+        return self.gamma * conv_apply(self.o, o.reshape(b, self.ch // 2, h, w)) + x

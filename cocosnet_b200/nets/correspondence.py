@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 from .. import corr as _corr
 from ..util import feature_normalize, vgg_preprocess
-from .blocks import BaseNetwork
+from .blocks import BaseNetwork, conv_apply
 from .generator import AdaptiveFeatureGenerator, DomainClassifier
 
 
@@ -30,8 +30,8 @@ class ResidualBlock(nn.Module):
         self.bn2 = nn.InstanceNorm2d(out_channels)
 
     def forward(self, x):
-        out = self.prelu(self.bn1(self.conv1(self.padding1(x))))
-        out = self.bn2(self.conv2(self.padding2(out)))
+        out = self.prelu(self.bn1(conv_apply(self.conv1, self.padding1(x))))
+        out = self.bn2(conv_apply(self.conv2, self.padding2(out)))
         return self.prelu(out + x)
 
 
@@ -63,7 +63,7 @@ class VGG19_feature_color_torchversion(nn.Module):
             blk, idx = int(name[4]), int(name[6])
             if blk > last:
                 break
-            x = F.relu(getattr(self, name)(x))
+            x = F.relu(conv_apply(getattr(self, name), x))
             out["r%d%d" % (blk, idx)] = x
             if all(k in out for k in out_keys):
                 break
@@ -140,7 +140,7 @@ class NoVGGCorrespondence(BaseNetwork):
         else:
             cont, ref = self.layer(feat_seg), self.layer(feat_img)
 
-        theta, phi = self.theta(cont), self.phi(ref)
+        theta, phi = conv_apply(self.theta, cont), conv_apply(self.phi, ref)
         if detach_flag:  # f.detach() at correspondence.py:292-293
             theta, phi = theta.detach(), phi.detach()
         res = _corr.correspondence_tail(

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .blocks import Attention, BaseNetwork, SPADEResnetBlock, equal_lr, nonspade_norm, norm_act
+from .blocks import Attention, BaseNetwork, SPADEResnetBlock, conv_apply, equal_lr, nonspade_norm, norm_act
 
 
 class SPADEGenerator(BaseNetwork):
@@ -38,7 +38,7 @@ class SPADEGenerator(BaseNetwork):
 
     def forward(self, input, warp_out=None):
         seg = input if warp_out is None else warp_out
-        x = self.fc(F.interpolate(seg, size=(self.sh, self.sw)))
+        x = conv_apply(self.fc, F.interpolate(seg, size=(self.sh, self.sw)))
         x = self.head_0(x, seg)
         x = self.G_middle_0(self.up(x), seg)
         x = self.G_middle_1(x, seg)

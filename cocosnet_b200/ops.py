@@ -8,6 +8,12 @@ import torch
 from . import _lib
 
 
+import os as _os
+
+# forward of stride-1 3x3 / 1x1 convolutions on the tcgen05 implicit-GEMM kernel (COCOS_NATIVE_CONV=0: cuDNN)
+NATIVE_CONV = _os.environ.get("COCOS_NATIVE_CONV", "1") != "0"
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
