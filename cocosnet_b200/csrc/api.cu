@@ -101,13 +101,14 @@ int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, 
   return norm_pack_launch(x, xt_workspace, out, B, C, h, w, match_kernel, eps, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Cp, int Cout,
-                   int KS, int pre_padded, void* stream) {
+int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
+                   int Cp, int Cout, int KS, int off, int bf16, void* stream) {
   if (!x || !wt || !y) {
     set_error("cocos_conv_fwd: null pointer argument");
     return -1;
   }
-  return conv_fwd_launch(x, wt, bias, y, B, H, W, Cp, Cout, KS, pre_padded, static_cast<cudaStream_t>(stream));
+  return conv_fwd_launch(x, wt, bias, y, B, H, W, Hin, Win, Cp, Cout, KS, off, bf16,
+                         static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@ constexpr int NUM_THREADS = 192;
 struct ConvParams {
   int B, H, W, Cout, Cp, KS, off;
   int TH, TW, tiles_h, tiles_w;
+  int bf16;           // operands are bf16 (backward-data path) instead of fp16
   const float* bias;  // [Cout] or null
   float* y;           // [B, Cout, H, W]
 };
@@ -99,7 +100,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
   } else if (warp == 5) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(BM, BN);
+    const uint32_t idesc = make_idesc_f16(BM, BN, p.bf16 != 0);
     uint32_t st = 0, ph = 0;
     for (int it = 0; it < iters; ++it) {
       mbar_wait(smem_u32(&bars->full[st]), ph);
@@ -150,15 +151,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 
 }  // namespace
 
-int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Cp, int Cout,
-                    int KS, int pre_padded, cudaStream_t stream) {
-  if (B <= 0 || H <= 0 || W <= 0 || Cp <= 0 || (Cp % BK) || Cout <= 0 || (KS != 1 && KS != 3)) {
-    set_error("conv_fwd: bad shape (B=%d H=%d W=%d Cp=%d Cout=%d KS=%d)", B, H, W, Cp, Cout, KS);
+int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
+                    int Cp, int Cout, int KS, int off, int bf16, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || Hin <= 0 || Win <= 0 || Cp <= 0 || (Cp % BK) || Cout <= 0 || (KS != 1 && KS != 3) ||
+      off < 0 || off >= 2 * KS) {
+    set_error("conv_fwd: bad shape (B=%d H=%d W=%d Hin=%d Win=%d Cp=%d Cout=%d KS=%d off=%d)", B, H, W, Hin, Win, Cp,
+              Cout, KS, off);
     return -1;
   }
   ConvParams p;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Cp = Cp; p.KS = KS;
-  p.off = pre_padded ? 0 : KS / 2;
+  p.off = off; p.bf16 = bf16;
   p.TW = W >= 128 ? 128 : W;
   p.TH = 128 / p.TW;
   if (p.TH > H) p.TH = H;
@@ -166,7 +169,6 @@ int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, 
   p.tiles_w = (W + p.TW - 1) / p.TW;
   p.tiles_h = (H + p.TH - 1) / p.TH;
   p.bias = bias; p.y = y;
-  const int Hin = pre_padded ? H + KS - 1 : H, Win = pre_padded ? W + KS - 1 : W;
   CUtensorMap tm_x, tm_w;
   const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
   const uint64_t pitches[3] = {(uint64_t)Cp * 2, (uint64_t)Win * Cp * 2, (uint64_t)Hin * Win * Cp * 2};

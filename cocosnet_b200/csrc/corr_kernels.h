@@ -38,8 +38,8 @@ int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int K
 int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cvp, int Nkp, int bf16,
                       cudaStream_t stream);
 
-int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Cp, int Cout,
-                    int KS, int pre_padded, cudaStream_t stream);
+int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
+                    int Cp, int Cout, int KS, int off, int bf16, cudaStream_t stream);
 
 int norm_pack_launch(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int mk, float eps,
                      cudaStream_t stream);

@@ -22,7 +22,7 @@ constexpr int TN = 32;  // positions per tile
 // split_mode 0: [h]; 1: [h, l, h] (query side); 2: [h, h, l] (key side)
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int N, int Kp, int split_mode,
-                 const float* __restrict__ rowscale) {
+                 const float* __restrict__ rowscale, int bf16) {
   __shared__ float tile[TC][TN + 1];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * TC;
@@ -51,7 +51,10 @@ pack_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C,
       const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
       const __half2 hi = __halves2half2(h0, h1);
       __half* row = d + static_cast<size_t>(n) * Kt + c;
-      if (!split_mode) {
+      if (bf16) {  // same 2-byte slots, bfloat16 rounding (gradient operands: fp32 range)
+        const __nv_bfloat162 bb = __floats2bfloat162_rn(x0, x1);
+        *reinterpret_cast<uint32_t*>(row) = *reinterpret_cast<const uint32_t*>(&bb);
+      } else if (!split_mode) {
         *reinterpret_cast<__half2*>(row) = hi;
       } else {
         const __half2 lo = __halves2half2(__float2half_rn(x0 - __half2float(h0)),
@@ -98,7 +101,7 @@ rowscale_kernel(const float* __restrict__ src, float* __restrict__ r, int C, int
 
 int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int Kp, int split_mode,
                          float* rowscale_out, cudaStream_t stream) {
-  if (B <= 0 || C <= 0 || N <= 0 || Kp < C || (Kp % 2) != 0 || split_mode < 0 || split_mode > 2) {
+  if (B <= 0 || C <= 0 || N <= 0 || Kp < C || (Kp % 2) != 0 || split_mode < 0 || (split_mode > 2 && split_mode != 4)) {
     set_error("pack_rows_f16: bad arguments (B=%d C=%d N=%d Kp=%d split=%d)", B, C, N, Kp, split_mode);
     return -1;
   }
@@ -107,7 +110,8 @@ int pack_rows_f16_launch(const float* src, void* dst, int B, int C, int N, int K
     COCOS_CUDA_CHECK(cudaGetLastError());
   }
   dim3 grid((N + TN - 1) / TN, (Kp + TC - 1) / TC, B);
-  pack_rows_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), C, N, Kp, split_mode, rowscale_out);
+  pack_rows_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), C, N, Kp, split_mode & 3, rowscale_out,
+                                             (split_mode & 4) != 0);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

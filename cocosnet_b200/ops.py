@@ -31,14 +31,16 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def pack_rows(x, kp=None, split=0, rowscale=False):
+def pack_rows(x, kp=None, split=0, rowscale=False, bf16=False):
     """fp32 [B,C,N] -> fp16 [B,N,Kt] (see cocos_pack_rows_f16).  With rowscale=True every
     position is scaled by r = 1/max_c|x| first and (packed, r [B,N]) is returned."""
     _req(x, torch.float32, "x")
     b, c, n = x.shape
     kp = round_up(c, 64) if kp is None else kp
     kt = kp * (3 if split else 1)
-    out = torch.empty((b, n, kt), dtype=torch.float16, device=x.device)
+    if bf16:
+        split = 4
+    out = torch.empty((b, n, kt), dtype=torch.bfloat16 if bf16 else torch.float16, device=x.device)
     r = torch.empty((b, n), dtype=torch.float32, device=x.device) if rowscale else None
     _lib.check(_lib.lib().cocos_pack_rows_f16(x.data_ptr(), out.data_ptr(), b, c, n, kp, split, _ptr(r), _stream()),
                "cocos_pack_rows_f16", kernels=2 if rowscale else 1)
@@ -232,14 +234,22 @@ def normalize_pack(x, match_kernel, eps):
     return out
 
 
-def pack_conv_weight(weight):
-    """[Cout, Cin, KS, KS] fp32 -> fp16 [Cout, KS*KS*Cp] with k = (r*KS + s)*Cp + c, Cp = Cin padded to 64."""
+def pack_conv_weight(weight, dtype=torch.float16):
+    """[Cout, Cin, KS, KS] fp32 -> [Cout, KS*KS*Cp] with k = (r*KS + s)*Cp + c, Cp = Cin padded to 64."""
     cout, cin, ks, _ = weight.shape
     cp = round_up(cin, 64)
     w = weight.permute(0, 2, 3, 1)
     if cp != cin:
         w = torch.nn.functional.pad(w, (0, cp - cin))
-    return w.reshape(cout, ks * ks * cp).to(torch.float16).contiguous()
+    return w.reshape(cout, ks * ks * cp).to(dtype).contiguous()
+
+
+def _conv_kernel(x16, wt, bias, b, h, w, hin, win, cp, cout, ks, off):
+    y = torch.empty((b, cout, h, w), dtype=torch.float32, device=x16.device)
+    bias_c = None if bias is None else bias.contiguous()
+    _lib.check(_lib.lib().cocos_conv_fwd(x16.data_ptr(), wt.data_ptr(), _ptr(bias_c), y.data_ptr(), b, h, w, hin, win, cp,
+                                         cout, ks, off, int(x16.dtype == torch.bfloat16), _stream()), "cocos_conv_fwd")
+    return y
 
 
 def conv_fwd_native(x, weight, bias, pre_padded):
@@ -252,32 +262,49 @@ def conv_fwd_native(x, weight, bias, pre_padded):
     h, w = (hin - ks + 1, win - ks + 1) if pre_padded else (hin, win)
     cp = round_up(cin, 64)
     x16 = pack_rows(x.view(b, cin, hin * win), kp=cp)  # == NHWC fp16 [B, Hin, Win, Cp]
-    wt = pack_conv_weight(weight)
-    y = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
-    bias_c = None if bias is None else bias.contiguous()
-    _lib.check(_lib.lib().cocos_conv_fwd(x16.data_ptr(), wt.data_ptr(), _ptr(bias_c), y.data_ptr(), b, h, w, cp, cout, ks,
-                                         int(bool(pre_padded)), _stream()), "cocos_conv_fwd")
-    return y
+    return _conv_kernel(x16, pack_conv_weight(weight), bias, b, h, w, hin, win, cp, cout, ks, 0 if pre_padded else ks // 2)
+
+
+def conv_dgrad_native(dy, weight, pre_padded):
+    """K2 backward-data with the SAME kernel: dx = conv(dy, flipped W^T) with zero halo (TMA out-of-bounds fill);
+    bf16 operands (gradients need fp32 range), fp32 accumulate.  dy [B,Cout,H,W] -> dx [B,Cin,Hin,Win]."""
+    dy = dy.contiguous()
+    _req(dy, torch.float32, "dy")
+    b, cout, h, w = dy.shape
+    _, cin, ks, _ = weight.shape
+    hin, win = (h + ks - 1, w + ks - 1) if pre_padded else (h, w)
+    cp = round_up(cout, 64)
+    dy16 = pack_rows(dy.view(b, cout, h * w), kp=cp, bf16=True)
+    wt = pack_conv_weight(weight.flip(2, 3).transpose(0, 1), dtype=torch.bfloat16)  # [Cin, KS*KS*Cout_p]
+    off = (ks - 1) if pre_padded else (ks - 1 - ks // 2)
+    return _conv_kernel(dy16, wt, None, b, hin, win, h, w, cp, cin, ks, off)
 
 
 class _ConvNative(torch.autograd.Function):
-    """conv2d (stride 1, KS in {1,3}) with the forward on the tcgen05 kernel; the backward (dgrad / wgrad) still goes
-    through aten.convolution_backward (cuDNN) -- K2 backward kernels are the next step."""
+    """conv2d (stride 1, KS in {1,3}): forward and backward-data on the tcgen05 implicit-GEMM kernel; the weight /
+    bias gradients still go through aten.convolution_backward (cuDNN wgrad) -- a split-K wgrad kernel is next."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pre_padded):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        ctx.pad = 0 if pre_padded else weight.shape[2] // 2
+        ctx.pre_padded = pre_padded
         return conv_fwd_native(x, weight, bias, pre_padded)
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
-        cout = weight.shape[0]
-        dx, dw, db = torch.ops.aten.convolution_backward(dy.contiguous(), x, weight, [cout] if ctx.has_bias else None,
-                                                         [1, 1], [ctx.pad, ctx.pad], [1, 1], False, [0, 0], 1, mask)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if need_x:
+            dx = conv_dgrad_native(dy, weight, ctx.pre_padded)
+        if need_w or need_b:
+            pad = 0 if ctx.pre_padded else weight.shape[2] // 2
+            _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.shape[0]] if ctx.has_bias else None,
+                                                            [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                            [False, need_w, need_b])
         return dx, dw, db, None
 
 

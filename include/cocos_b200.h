@@ -30,7 +30,7 @@ const char* cocos_last_error(void);
  * fp16 [B, N, Kt], Kt = Kp * (split_mode ? 3 : 1), Kp >= C zero padded, Kp%2==0.
  * This is the `theta.permute(0, 2, 1)` of correspondence.py:281 plus the
  * operand rounding.  split_mode: 0 = plain fp16; 1 = query side [hi, lo, hi];
- * 2 = key side [hi, hi, lo] (one GEMM then sums hi*hi + lo*hi + hi*lo).
+ * 2 = key side [hi, hi, lo] (one GEMM then sums hi*hi + lo*hi + hi*lo); 4 = plain bf16 instead of fp16.
  * rowscale_out (may be NULL): if given, every position n is first multiplied by
  * r[b,n] = 1 / max_c |src[b,c,n]| and r is written to rowscale_out [B,N] (used for
  * the upstream gradient dO in the backward so it always fits fp16). */
@@ -99,11 +99,14 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
 
 /* K2: TMA-fed tcgen05 implicit-GEMM convolution, forward, KS in {1, 3}, stride 1 (the 3x3 convs of the SPADE blocks,
  * domain adaptor and residual blocks: architecture.py:31-33,73-74; normalization.py:112-120; correspondence.py:17-22).
- * x  : fp16 NHWC [B, Hin, Win, Cp], Cp % 64 == 0 (cocos_pack_rows_f16 of the NCHW activation viewed as [B,C,Hin*Win]).
- *      pre_padded != 0: Hin = H + KS - 1, the (reflection) halo is already in x; else Hin = H and the halo is zero.
- * wt : fp16 [Cout, KS*KS*Cp], k = (r*KS + s)*Cp + c.   bias: fp32 [Cout] or NULL.   y: fp32 NCHW [B, Cout, H, W]. */
-int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Cp, int Cout,
-                   int KS, int pre_padded, void* stream);
+ *   y[b,n,h,w] = bias[n] + sum_{r,s,c} x[b, h + r - off, w + s - off, c] * wt[n, (r*KS + s)*Cp + c]
+ * x  : fp16 (bf16 if `bf16`) NHWC [B, Hin, Win, Cp], Cp % 64 == 0 (cocos_pack_rows_f16 of the NCHW tensor viewed as
+ *      [B,C,Hin*Win]); reads outside [0,Hin)x[0,Win) are zero (TMA out-of-bounds fill).
+ *      forward, producer already padded (reflection): Hin = H + KS - 1, off = 0; forward with zero padding: Hin = H,
+ *      off = KS/2; backward-data (the same kernel): x = dy, wt = spatially flipped W^T, off = KS - 1 (- padding).
+ * wt : fp16/bf16 [Cout, KS*KS*Cp].   bias: fp32 [Cout] or NULL.   y: fp32 NCHW [B, Cout, H, W]. */
+int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
+                   int Cp, int Cout, int KS, int off, int bf16, void* stream);
 
 /* Fused operand prologue for `--PONO_C` (correspondence.py:273-281 / 283-289): x fp32 [B,C,h,w] (output of the theta
  * or phi 1x1 conv) -> unfold(match_kernel, zero pad) -> minus the mean over K = C*mk*mk -> / (L2 norm over K + eps)

@@ -352,7 +352,8 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", CONV_CASES)
 def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_padded):
-    """K2 forward (tcgen05 implicit GEMM, fp16 operands) vs torch conv2d in fp64; backward through cuDNN."""
+    """K2 forward (tcgen05 implicit GEMM, fp16 operands) vs torch conv2d in fp64; backward-data on the same kernel
+    (bf16 operands: 2^-9 relative rounding on dy and W -> ~2e-3 rel-L2), weight/bias gradients through cuDNN."""
     import torch.nn.functional as F
     from cocosnet_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(cin + h)
@@ -372,6 +373,6 @@ def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_pad
     wr = wgt.detach().clone().requires_grad_(True)
     br = bias.detach().clone().requires_grad_(True)
     F.conv2d(xr, wr, br, padding=0 if pre_padded else pad).backward(dy)
-    assert _rel(xin.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-3
+    assert _rel(xin.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 4e-3
     assert _rel(wgt.grad.cpu().numpy(), wr.grad.cpu().numpy()) < 2e-3
     assert _rel(bias.grad.cpu().numpy(), br.grad.cpu().numpy()) < 1e-4

@@ -29,7 +29,7 @@ for (cin, cout, hw) in ((1024, 1024, 8), (1024, 1024, 16), (512, 512, 32), (256,
     y = torch.empty(b, cout, hw, hw, device="cuda")
     from cocosnet_b200 import _lib
     def kern():
-        _lib.check(_lib.lib().cocos_conv_fwd(x16.data_ptr(), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), b, hw, hw, cp, cout, 3, 1,
+        _lib.check(_lib.lib().cocos_conv_fwd(x16.data_ptr(), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), b, hw, hw, hw + 2, hw + 2, cp, cout, 3, 0, 0,
                                              torch.cuda.current_stream().cuda_stream), "conv")
     m_kern = t(kern)
     print("cin %4d cout %4d %3dx%-3d  cudnn tf32 %.3f ms (%.0f TF)  native total %.3f ms  kernel only %.3f ms (%.0f TF)" % (
