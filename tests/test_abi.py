@@ -19,6 +19,30 @@ def test_header_symbols_exported():
     assert h.cocos_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_arity_and_kinds():
+    """Every ctypes argtypes list in _lib.SIGNATURES has the arity and pointer/int/float kinds of the C prototype."""
+    import ctypes
+    from cocosnet_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "cocos_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(cocos_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p, a in zip(params, argtypes):
+            if "*" in p:
+                assert a is ctypes.c_void_p, (name, p)
+            elif p.startswith("long long"):
+                assert a in (ctypes.c_longlong, ctypes.c_long) and ctypes.sizeof(a) == 8, (name, p)
+            elif p.startswith("float"):
+                assert a is ctypes.c_float, (name, p)
+            else:
+                assert a is ctypes.c_int, (name, p)
+
+
 def test_bad_arguments_are_errors_not_crashes():
     from cocosnet_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
