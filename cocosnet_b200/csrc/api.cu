@@ -101,6 +101,24 @@ int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, 
   return norm_pack_launch(x, xt_workspace, out, B, C, h, w, match_kernel, eps, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_cast_pitch(const float* src, void* dst, long long rows, int W, int Wp, int bf16, void* stream) {
+  if (!src || !dst) {
+    set_error("cast_pitch: null pointer");
+    return -1;
+  }
+  return cast_pitch_launch(src, dst, rows, W, Wp, bf16, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
+                     int KS, int off, int dy_bf16, int x_bf16, void* stream) {
+  if (!dy || !x || !ws) {
+    set_error("conv_wgrad: null pointer");
+    return -1;
+  }
+  return conv_wgrad_launch(dy, x, ws, B, H, W, Hin, Win, Cout, Cin, KS, off, dy_bf16, x_bf16,
+                           static_cast<cudaStream_t>(stream));
+}
+
 int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
                    int Cp, int Cout, int KS, int off, int bf16, void* stream) {
   if (!x || !wt || !y) {

@@ -280,9 +280,42 @@ def conv_dgrad_native(dy, weight, pre_padded):
     return _conv_kernel(dy16, wt, None, b, hin, win, h, w, cp, cin, ks, off)
 
 
+def cast_pitch(x, bf16):
+    """fp32 [..., W] -> fp16/bf16 [..., Wp] with Wp = W rounded up to 8 (pad columns are never read)."""
+    x = x.contiguous()
+    _req(x, torch.float32, "x")
+    w = x.shape[-1]
+    wp = round_up(w, 8)
+    out = torch.empty(x.shape[:-1] + (wp,), dtype=torch.bfloat16 if bf16 else torch.float16, device=x.device)
+    _lib.check(_lib.lib().cocos_cast_pitch(x.data_ptr(), out.data_ptr(), x.numel() // w, w, wp, int(bf16), _stream()),
+               "cocos_cast_pitch")
+    return out
+
+
+WGRAD_X_BF16 = _os.environ.get("COCOS_WGRAD_X_BF16", "0") == "1"
+
+
+def conv_wgrad_native(dy, x, ks, pre_padded):
+    """K2w backward-weights: dW [Cout,Cin,KS,KS] = sum over pixels of dy (bf16) x shifted x (fp16), fp32 accumulate,
+    on the split-K tcgen05 kernel.  dy [B,Cout,H,W], x [B,Cin,Hin,Win] fp32 NCHW."""
+    b, cout, h, w = dy.shape
+    _, cin, hin, win = x.shape
+    dy16 = cast_pitch(dy, True)
+    x16 = cast_pitch(x, WGRAD_X_BF16)
+    ws = torch.empty((ks * ks, cin, cout), dtype=torch.float32, device=dy.device)
+    _lib.check(_lib.lib().cocos_conv_wgrad(dy16.data_ptr(), x16.data_ptr(), ws.data_ptr(), b, h, w, hin, win, cout, cin,
+                                           ks, 0 if pre_padded else ks // 2, 1, int(WGRAD_X_BF16), _stream()),
+               "cocos_conv_wgrad")
+    return ws.view(ks, ks, cin, cout).permute(3, 2, 0, 1).contiguous()
+
+
+NATIVE_WGRAD = _os.environ.get("COCOS_NATIVE_WGRAD", "1") == "1"
+NATIVE_DGRAD = _os.environ.get("COCOS_NATIVE_DGRAD", "1") == "1"
+
+
 class _ConvNative(torch.autograd.Function):
-    """conv2d (stride 1, KS in {1,3}): forward and backward-data on the tcgen05 implicit-GEMM kernel; the weight /
-    bias gradients still go through aten.convolution_backward (cuDNN wgrad) -- a split-K wgrad kernel is next."""
+    """conv2d (stride 1, KS in {1,3}): forward, backward-data and backward-weights on the tcgen05 implicit-GEMM
+    kernels (conv.cu, conv_wgrad.cu); COCOS_NATIVE_WGRAD=0 sends the weight gradient through cuDNN instead."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pre_padded):
@@ -298,13 +331,22 @@ class _ConvNative(torch.autograd.Function):
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         dy = dy.contiguous()
         dx = dw = db = None
-        if need_x:
+        if need_x and NATIVE_DGRAD:
             dx = conv_dgrad_native(dy, weight, ctx.pre_padded)
-        if need_w or need_b:
+            need_x = False
+        if need_w and NATIVE_WGRAD:
+            dw = conv_wgrad_native(dy, x, weight.shape[2], ctx.pre_padded)
+            if need_b:
+                db = dy.sum((0, 2, 3))
+            need_w = need_b = False
+        if need_x or need_w or need_b:
             pad = 0 if ctx.pre_padded else weight.shape[2] // 2
-            _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.shape[0]] if ctx.has_bias else None,
+            dx2, dw2, db2 = torch.ops.aten.convolution_backward(dy, x, weight, [weight.shape[0]] if ctx.has_bias else None,
                                                             [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
-                                                            [False, need_w, need_b])
+                                                            [need_x, need_w, need_b])
+            dx = dx2 if need_x else dx
+            dw = dw2 if need_w else dw
+            db = db2 if need_b else db
         return dx, dw, db, None
 
 

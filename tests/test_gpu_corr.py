@@ -374,5 +374,5 @@ def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_pad
     br = bias.detach().clone().requires_grad_(True)
     F.conv2d(xr, wr, br, padding=0 if pre_padded else pad).backward(dy)
     assert _rel(xin.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 4e-3
-    assert _rel(wgt.grad.cpu().numpy(), wr.grad.cpu().numpy()) < 2e-3
+    assert _rel(wgt.grad.cpu().numpy(), wr.grad.cpu().numpy()) < 4e-3
     assert _rel(bias.grad.cpu().numpy(), br.grad.cpu().numpy()) < 1e-4

@@ -44,12 +44,15 @@ def main():
     torch.cuda.synchronize()
     print("step ms: %.2f  (%.2f img/s at B=%d)  peak mem %.1f GB" % (s.elapsed_time(e) / 3, args.b * 3e3 / s.elapsed_time(e),
                                                               args.b, torch.cuda.max_memory_allocated() / 2 ** 30))
-    if args.no_table:
-        return
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step()
         torch.cuda.synchronize()
+    ka = prof.key_averages()
+    busy = sum(k.self_device_time_total for k in ka) / 1e3
+    print("GPU busy (sum of kernel durations) %.2f ms; launches %d" % (busy, sum(k.count for k in ka if k.self_device_time_total > 0)))
+    if args.no_table:
+        return
     print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=args.rows, max_name_column_width=70))
 
 
