@@ -101,12 +101,13 @@ int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, 
   return norm_pack_launch(x, xt_workspace, out, B, C, h, w, match_kernel, eps, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_cast_pitch(const float* src, void* dst, long long rows, int W, int Wp, int bf16, void* stream) {
+int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,
+                     int bf16, void* stream) {
   if (!src || !dst) {
     set_error("cast_pitch: null pointer");
     return -1;
   }
-  return cast_pitch_launch(src, dst, rows, W, Wp, bf16, static_cast<cudaStream_t>(stream));
+  return cast_pitch_launch(src, dst, rows, Win, Wout, Wp, nshift, off, bf16, static_cast<cudaStream_t>(stream));
 }
 
 int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,

@@ -6,10 +6,12 @@
 // Both operands are K-major with K = pixels, which is exactly what NCHW gives for free:
 //   * A tile = dY, 16-bit NCHW [B, Cout, H, Wp]: one 4-D TMA box {bw, bh, 128, 1} = 64 pixels (bh rows of bw) of 128
 //     channels; each channel's 64 pixels land as one 128-byte swizzled row -- the tcgen05 K-major layout.
-//   * B tile = X, 16-bit NCHW [B, Cin, Hin, Winp]: the same box shifted by the tap, {bw, bh, BN, 1} at
-//     (w0 + s - off, h0 + r - off, c0, b); zero padding and ragged edges are TMA out-of-bounds zero fill (a pixel that
-//     does not exist has dY == 0 from the same fill, so it contributes nothing).
-//   * Wp / Winp: row pitch rounded up to 8 elements (TMA needs 16-byte strides); cocos_cast_pitch makes those copies.
+//   * B tile = X, 16-bit [KS][B, Cin, Hin, Wp]: KS column-shifted NCHW copies (copy s holds columns s-off .. s-off+W-1;
+//     a TMA box has to start on a 16-byte boundary of the innermost dimension, so the tap's column shift is baked into
+//     the copy and only the row shift is a coordinate): box {bw, bh, BN, 1} at (w0, h0 + r - off, c0, s*B + b).
+//     Rows outside the image and ragged edges are TMA out-of-bounds zero fill (a pixel that does not exist has
+//     dY == 0 from the same fill, so it contributes nothing).
+//   * Wp: row pitch rounded up to 8 elements (TMA needs 16-byte strides); cocos_cast_pitch makes all these copies.
 //   * the pixel range is split over gridDim.z (split-K) so that every layer fills the 148 SMs; partial tiles are added
 //     into ws[tap][c][n] (fp32, n contiguous -> coalesced red.global.add), which the host permutes to [n][c][r][s].
 // dY is bf16 (gradient range), X fp16 or bf16 (instruction descriptor carries the two formats separately).
@@ -106,7 +108,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         mbar_expect_tx(full, ATOM_BYTES + (BN / 128) * ATOM_BYTES);
         const int w0 = cw * p.bw, h0 = ch * p.bh;
         tma_load_4d(smem0 + st * STAGE_BYTES, &tm_dy, full, w0, h0, n0, b);
-        tma_load_4d(smem0 + st * STAGE_BYTES + ATOM_BYTES, &tm_x, full, w0 + s - p.off, h0 + r - p.off, c0, b);
+        tma_load_4d(smem0 + st * STAGE_BYTES + ATOM_BYTES, &tm_x, full, w0, h0 + r - p.off, c0, s * p.B + b);
         if (++st == STAGES) { st = 0; ph ^= 1; }
         if (++cw == p.chunks_w) {
           cw = 0;
@@ -166,47 +168,46 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   }
 }
 
-// fp32 [rows, W] -> 16-bit [rows, Wp] (Wp >= W, pad columns left untouched: the tensor maps never read them)
+// fp32 [rows, Win] -> 16-bit [nshift, rows, Wp]: copy s holds dst[s][row][w] = src[row][w + s - off] for w < Wout (zero
+// where that column does not exist).  Pad columns w >= Wout are left untouched: the tensor maps never read them.
+// nshift = 1, off = 0, Wout = Win is a plain cast with a padded pitch.
 __global__ void __launch_bounds__(256)
-cast_pitch_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int W, int Wp, int bf16) {
-  const int wq = (W + 3) >> 2;
+cast_pitch_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int Win, int Wout, int Wp,
+                  int nshift, int off, int bf16) {
+  const int wq = (Wout + 3) >> 2;
   const long long total = rows * wq;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
     const long long row = i / wq;
     const int w = static_cast<int>(i - row * wq) * 4;
-    const float* sp = src + row * W + w;
-    uint16_t* dp = dst + row * Wp + w;
-    float x[4];
-    if (w + 4 <= W && (W & 3) == 0) {
-      const float4 v = *reinterpret_cast<const float4*>(sp);
-      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-    } else {
+    const float* sp = src + row * Win;
+    for (int s = 0; s < nshift; ++s) {
+      uint16_t o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = (w + j < W) ? sp[j] : 0.f;
-    }
-    uint16_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(x[j])) : __half_as_ushort(__float2half_rn(x[j]));
-    if (w + 4 <= Wp) {  // Wp % 8 == 0 and w % 4 == 0: 8-byte aligned
-      *reinterpret_cast<uint2*>(dp) = make_uint2(o[0] | (uint32_t(o[1]) << 16), o[2] | (uint32_t(o[3]) << 16));
-    } else {
-      for (int j = 0; j < 4 && w + j < Wp; ++j) dp[j] = o[j];
+      for (int j = 0; j < 4; ++j) {
+        const int col = w + j + s - off;
+        const float x = (w + j < Wout && col >= 0 && col < Win) ? __ldg(sp + col) : 0.f;
+        o[j] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(x)) : __half_as_ushort(__float2half_rn(x));
+      }
+      // Wp % 8 == 0 and w % 4 == 0: the 8-byte store is aligned and stays inside the padded row
+      *reinterpret_cast<uint2*>(dst + (static_cast<long long>(s) * rows + row) * Wp + w) =
+          make_uint2(o[0] | (uint32_t(o[1]) << 16), o[2] | (uint32_t(o[3]) << 16));
     }
   }
 }
 
 }  // namespace
 
-int cast_pitch_launch(const float* src, void* dst, long long rows, int W, int Wp, int bf16, cudaStream_t stream) {
-  if (rows <= 0 || W <= 0 || Wp < W || (Wp % 8) != 0) {
-    set_error("cast_pitch: bad shape (rows=%lld W=%d Wp=%d)", rows, W, Wp);
+int cast_pitch_launch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,
+                      int bf16, cudaStream_t stream) {
+  if (rows <= 0 || Win <= 0 || Wout <= 0 || Wp < Wout || (Wp % 8) != 0 || nshift < 1 || nshift > 3 || off < 0) {
+    set_error("cast_pitch: bad shape (rows=%lld Win=%d Wout=%d Wp=%d nshift=%d off=%d)", rows, Win, Wout, Wp, nshift, off);
     return -1;
   }
-  const long long total = rows * ((W + 3) / 4);
+  const long long total = rows * ((Wout + 3) / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cast_pitch_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), rows, W, Wp, bf16);
+  cast_pitch_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), rows, Win, Wout, Wp,
+                                                                  nshift, off, bf16);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -240,7 +241,8 @@ int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, in
   p.splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;  // no empty CTA
   if (p.splits > 1) COCOS_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(float) * taps * Cin * Cout, stream));
 
-  const int Wp = (W + 7) / 8 * 8, Winp = (Win + 7) / 8 * 8;
+  const int Wp = (W + 7) / 8 * 8;
+  (void)Win;
   CUtensorMap tm_dy, tm_x;
   int rc;
   {
@@ -250,8 +252,10 @@ int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, in
     if ((rc = make_tmap_f16_4d(&tm_dy, dy, dims, pitches, box))) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)Win, (uint64_t)Hin, (uint64_t)Cin, (uint64_t)B};
-    const uint64_t pitches[3] = {(uint64_t)Winp * 2, (uint64_t)Hin * Winp * 2, (uint64_t)Cin * Hin * Winp * 2};
+    // x arrives as KS column-shifted copies [KS][B][Cin][Hin][Wp] (copy s starts at column s - off), because a TMA
+    // box must start on a 16-byte boundary of the innermost dimension: the tap's column shift cannot be a coordinate.
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Hin, (uint64_t)Cin, (uint64_t)B * KS};
+    const uint64_t pitches[3] = {(uint64_t)Wp * 2, (uint64_t)Hin * Wp * 2, (uint64_t)Cin * Hin * Wp * 2};
     const uint32_t box[4] = {(uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)(BN > 256 ? 256 : BN), 1};
     if ((rc = make_tmap_f16_4d(&tm_x, x, dims, pitches, box))) return rc;
   }

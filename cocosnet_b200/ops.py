@@ -280,15 +280,18 @@ def conv_dgrad_native(dy, weight, pre_padded):
     return _conv_kernel(dy16, wt, None, b, hin, win, h, w, cp, cin, ks, off)
 
 
-def cast_pitch(x, bf16):
-    """fp32 [..., W] -> fp16/bf16 [..., Wp] with Wp = W rounded up to 8 (pad columns are never read)."""
+def cast_pitch(x, bf16, wout=None, nshift=1, off=0):
+    """fp32 [..., Win] -> fp16/bf16 [nshift, ..., Wp]: copy s holds columns s-off .. s-off+wout-1 (zero where they do
+    not exist), row pitch Wp = wout rounded up to 8 (pad columns are never read)."""
     x = x.contiguous()
     _req(x, torch.float32, "x")
-    w = x.shape[-1]
-    wp = round_up(w, 8)
-    out = torch.empty(x.shape[:-1] + (wp,), dtype=torch.bfloat16 if bf16 else torch.float16, device=x.device)
-    _lib.check(_lib.lib().cocos_cast_pitch(x.data_ptr(), out.data_ptr(), x.numel() // w, w, wp, int(bf16), _stream()),
-               "cocos_cast_pitch")
+    win = x.shape[-1]
+    wout = win if wout is None else wout
+    wp = round_up(wout, 8)
+    out = torch.empty((nshift,) + tuple(x.shape[:-1]) + (wp,), dtype=torch.bfloat16 if bf16 else torch.float16,
+                      device=x.device)
+    _lib.check(_lib.lib().cocos_cast_pitch(x.data_ptr(), out.data_ptr(), x.numel() // win, win, wout, wp, nshift, off,
+                                           int(bf16), _stream()), "cocos_cast_pitch")
     return out
 
 
@@ -301,7 +304,7 @@ def conv_wgrad_native(dy, x, ks, pre_padded):
     b, cout, h, w = dy.shape
     _, cin, hin, win = x.shape
     dy16 = cast_pitch(dy, True)
-    x16 = cast_pitch(x, WGRAD_X_BF16)
+    x16 = cast_pitch(x, WGRAD_X_BF16, wout=w, nshift=ks, off=0 if pre_padded else ks // 2)
     ws = torch.empty((ks * ks, cin, cout), dtype=torch.float32, device=dy.device)
     _lib.check(_lib.lib().cocos_conv_wgrad(dy16.data_ptr(), x16.data_ptr(), ws.data_ptr(), b, h, w, hin, win, cout, cin,
                                            ks, 0 if pre_padded else ks // 2, 1, int(WGRAD_X_BF16), _stream()),

@@ -108,16 +108,20 @@ int cocos_spade_mod_bwd(const float* dy, const float* x, const float* gb, const 
 int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
                    int Cp, int Cout, int KS, int off, int bf16, void* stream);
 
-/* fp32 [rows, W] -> 16-bit (fp16, or bf16 if `bf16`) [rows, Wp] with the row pitch Wp >= W, Wp % 8 == 0 (TMA needs
- * 16-byte strides).  Makes the NCHW 16-bit operand copies of cocos_conv_wgrad. */
-int cocos_cast_pitch(const float* src, void* dst, long long rows, int W, int Wp, int bf16, void* stream);
+/* fp32 [rows, Win] -> 16-bit (fp16, or bf16 if `bf16`) [nshift, rows, Wp], row pitch Wp >= Wout, Wp % 8 == 0 (TMA
+ * needs 16-byte strides): dst[s][row][w] = src[row][w + s - off] for w < Wout, zero where that column does not exist.
+ * Makes the NCHW 16-bit operand copies of cocos_conv_wgrad (dy: nshift 1, off 0; x: nshift KS column-shifted copies,
+ * because a TMA box cannot start at an odd column). */
+int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,
+                     int bf16, void* stream);
 
 /* K2w: convolution backward-weights (stride 1, KS in {1,3}) as a tcgen05 GEMM over the B*H*W pixels, split-K over the
  * grid.  Replaces the wgrad half of autograd's convolution_backward for the same nn.Conv2d call sites as
  * cocos_conv_fwd.
  *   ws[(r*KS + s), c, n] = sum_{b,h,w} dy[b, n, h, w] * x[b, c, h + r - off, w + s - off]
- * dy : 16-bit NCHW [B, Cout, H, Wp]  (Wp = W rounded up to 8);  x : 16-bit NCHW [B, Cin, Hin, Winp] (same rounding);
- *      reads outside [0,Hin)x[0,Win) are zero.  off = 0 when x carries its halo, KS/2 for zero padding.
+ * dy : 16-bit NCHW [B, Cout, H, Wp]  (Wp = W rounded up to 8);
+ * x  : 16-bit [KS, B, Cin, Hin, Wp], the KS column-shifted copies cocos_cast_pitch(.., Win, W, Wp, KS, off, ..) makes;
+ *      rows outside [0,Hin) are zero.  off = 0 when x carries its halo, KS/2 for zero padding.
  * ws : fp32 [KS*KS, Cin, Cout], fully overwritten (zeroed + atomically accumulated when the pixel range is split). */
 int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
                      int KS, int off, int dy_bf16, int x_bf16, void* stream);
