@@ -295,7 +295,7 @@ def cast_pitch(x, bf16, wout=None, nshift=1, off=0):
     return out
 
 
-WGRAD_X_BF16 = _os.environ.get("COCOS_WGRAD_X_BF16", "0") == "1"
+WGRAD_X_BF16 = _os.environ.get("COCOS_WGRAD_X_BF16", "1") == "1"  # mixed bf16 x fp16 operands are an illegal instruction
 
 
 def conv_wgrad_native(dy, x, ks, pre_padded):
@@ -337,7 +337,7 @@ class _ConvNative(torch.autograd.Function):
         if need_x and NATIVE_DGRAD:
             dx = conv_dgrad_native(dy, weight, ctx.pre_padded)
             need_x = False
-        if need_w and NATIVE_WGRAD:
+        if need_w and NATIVE_WGRAD and dy.shape[3] >= 64 and x.shape[1] >= 128:  # K2w takes the wide layers
             dw = conv_wgrad_native(dy, x, weight.shape[2], ctx.pre_padded)
             if need_b:
                 db = dy.sum((0, 2, 3))

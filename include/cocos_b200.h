@@ -122,6 +122,8 @@ int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int W
  * dy : 16-bit NCHW [B, Cout, H, Wp]  (Wp = W rounded up to 8);
  * x  : 16-bit [KS, B, Cin, Hin, Wp], the KS column-shifted copies cocos_cast_pitch(.., Win, W, Wp, KS, off, ..) makes;
  *      rows outside [0,Hin) are zero.  off = 0 when x carries its halo, KS/2 for zero padding.
+ * W >= 64 only (narrower layers: error return; the host mirror sends them to the library wgrad); both operands bf16
+ * (dy_bf16 = x_bf16 = 1): a bf16 x fp16 instruction descriptor is rejected by the hardware.
  * ws : fp32 [KS*KS, Cin, Cout], fully overwritten (zeroed + atomically accumulated when the pixel range is split). */
 int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
                      int KS, int off, int dy_bf16, int x_bf16, void* stream);

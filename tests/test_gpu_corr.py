@@ -346,8 +346,37 @@ CONV_CASES = [
     (1, 64, 64, 256, 256, 3, True),     # up_3 resolution
     (2, 256, 32, 20, 12, 1, False),     # 1x1, ragged patch
     (2, 96, 200, 20, 12, 3, False),     # zero padding by TMA out-of-bounds fill, ragged everything
-    (1, 512, 512, 64, 64, 3, False),
+    (1, 512, 512, 64, 64, 3, False),    # wide layer: backward-weights on K2w as well
+    (2, 128, 96, 72, 80, 3, True),      # K2w with a ragged width (80 = 64 + 16) and pre-padded input
+    (1, 154, 128, 128, 128, 3, True),   # K2w, Cin tile of 256 over 154 channels
 ]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", [(2, 64, 64, 64, 128, 3, True), (2, 32, 200, 70, 64, 1, False),
+                                                         (1, 300, 130, 64, 64, 3, False)])
+def test_conv_wgrad_native_direct(b, cin, cout, h, w, ks, pre_padded):
+    """K2w (split-K tcgen05 backward-weights, bf16 operands) vs autograd in fp64, including the narrow-channel tiles
+    the model path does not route to it."""
+    import torch.nn.functional as F
+    from cocosnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(cin + w)
+    pad = ks // 2
+    hin, win = (h + 2 * pad, w + 2 * pad) if pre_padded else (h, w)
+    x = torch.randn(b, cin, hin, win, device="cuda", generator=g)
+    dy = torch.randn(b, cout, h, w, device="cuda", generator=g)
+    dw = ops.conv_wgrad_native(dy, x, ks, pre_padded)
+    wr = torch.zeros(cout, cin, ks, ks, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wr, None, padding=0 if pre_padded else pad).backward(dy.double())
+    assert dw.shape == wr.shape
+    assert _rel(dw.cpu().numpy(), wr.grad.cpu().numpy()) < 4e-3
+
+
+def test_conv_wgrad_rejects_narrow_layers():
+    from cocosnet_b200 import _lib, ops
+    x = torch.randn(1, 64, 18, 18, device="cuda")
+    dy = torch.randn(1, 64, 16, 16, device="cuda")
+    with pytest.raises(_lib.CocosError):
+        ops.conv_wgrad_native(dy, x, 3, True)
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", CONV_CASES)
