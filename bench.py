@@ -112,7 +112,7 @@ def k1_roofline(torch, batch=8, n=4096, kd=256, cv=3, iters=20):
     summ = os.path.join(ROOT, "profiles", "k1_fwd_ncu_summary.json")
     if os.path.exists(summ):
         traffic = json.load(open(summ)).get("dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "corr_fwd_kernel (fused correlation+softmax+warp)", "achieved": achieved,
+    return {"bound": "tensor", "kernel": "corr_fwd4_kernel (fused correlation+softmax+warp)", "achieved": achieved,
             "peak": peak, "peak_source": src + " cuBLAS bf16 burst", "unit": "TFLOP/s", "frac": achieved / peak,
             "frac_of_nominal_2250": achieved / 2250.0, "traffic": traffic,
             "shape": {"batch": batch, "HW": n, "C": kd, "Cv": cv}, "ms_per_launch": ms,
@@ -207,13 +207,13 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
 
     def step_resident():
-        trainer.run_generator_one_step(dev)
-        trainer.run_discriminator_one_step(dev)
+        trainer.run_step(dev)  # one GPU: CUDA-graph replay after the first eager iterations (trainer.run_step)
 
     def step_e2e():
-        d = {k: (v.cuda(non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-        trainer.run_generator_one_step(d)
-        trainer.run_discriminator_one_step(d)
+        if trainer._graph is not None:  # pinned host batch -> the graph's static input buffers -> replay
+            trainer.run_step(host)
+        else:
+            trainer.run_step({k: (v.cuda(non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()})
         losses = torch.stack([v.mean().reshape(()) for v in trainer.get_latest_losses().values()])
         return losses.cpu()  # D2H read of the step's result
 
@@ -234,12 +234,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if trainer.graph_capable():  # eager iterations + the capture happen before the counted warm-up
+        for _ in range(trainer.GRAPH_WARMUP + 1):
+            step_resident()
     for _ in range(warmup):
         step_resident()
+    graphed = trainer._graph is not None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = _lib.LAUNCHES
     ms = timed(step_resident, args.steps)
-    launches = _lib.LAUNCHES - l0
+    launches = trainer.graph_native_launches * args.steps if graphed else _lib.LAUNCHES - l0
     clocks = sampler.stop() if sampler else None
     if profile_mode:
         print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": launches}))
@@ -261,11 +265,12 @@ def main():
         gb = PER_GPU_BATCH * world
         line = {"metric": METRIC, "value": gb * args.steps / (ms / 1e3), "unit": "images/sec", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands (fused correspondence/attention) + tf32 convs, fp32 accumulate",
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (forward) / bf16 (backward) operands on tcgen05 for correspondence, attention and stride-1 convs; tf32 for the remaining library convs; fp32 accumulate",
                 "data": "synthetic",
                 "config": {"workload": "ade20k 256x256 --use_attention --maskmix --PONO --PONO_C, full G+D train step "
                                        "(fwd+bwd+Adam), match_kernel 3 (K=2304), BASELINE configs[1]",
                            "global_batch": gb, "per_gpu_batch": PER_GPU_BATCH, "parallelism": "dp%d" % world,
+                           "cuda_graph": graphed if trainer.graph_error is None else "capture failed: " + trainer.graph_error,
                            "l2": "per-step activations (multi-GB) and inputs exceed the 126 MB L2; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": gb * args.steps / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,

@@ -6,6 +6,10 @@ the batch (what DataParallel.scatter does) and the gradients are summed with
 ONE bucketed NCCL all-reduce per optimiser step (G+Corr grads on the G step, D
 grads on the D step) and divided by the world size -- the reference's
 `sum(losses).mean()` over replicas.  No per-step parameter broadcast.
+
+`run_step` is the launch-bound answer for one GPU: the whole G+D iteration (both forwards, both backwards, both
+fused-Adam updates: ~12 000 kernel launches, which the Python/ATen dispatcher cannot issue as fast as a B200 retires
+them) is captured ONCE into a CUDA graph after a few eager iterations and replayed from static input buffers.
 """
 import os
 
@@ -104,6 +108,65 @@ class Pix2PixTrainer:
             self._g_params = [p for k in ("netG", "netCorr") for p in net[k].parameters()]
             self._d_params = [p for p in net["netD"].parameters()]
         self.g_losses, self.d_losses, self.out = {}, {}, {}
+        self._graph, self._static_in, self._eager_steps = None, None, 0
+        self.graph_native_launches = 0
+        self.graph_error = None
+
+    # ------------------------------------------------------------------ CUDA-graph step (one GPU)
+    GRAPH_WARMUP = 3  # eager iterations before the capture (cuDNN autotuning, lazy state, allocator warm-up)
+
+    def graph_capable(self):
+        return (self.opt.isTrain and len(self.opt.gpu_ids) > 0 and _world() == 1
+                and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
+
+    def _eager_step(self, data, alpha=1):
+        self.run_generator_one_step(data, alpha)
+        self.run_discriminator_one_step(data)
+
+    def _load_static(self, data):
+        for k, buf in self._static_in.items():
+            buf.copy_(data[k], non_blocking=True)
+
+    def run_step(self, data, alpha=1):
+        """One full training iteration (== run_generator_one_step + run_discriminator_one_step, train.py:55-59).
+        Every call is exactly one optimiser step of G and of D.  On one GPU the first GRAPH_WARMUP calls run eagerly,
+        the next one captures the iteration into a CUDA graph, and from then on a call is: copy the batch into the
+        static input buffers (host or device source) + one graph launch.  `alpha`, the learning rates and the batch
+        shapes are baked into the graph (update_learning_rate drops it; it is re-captured on the next call)."""
+        if not self.graph_capable():
+            return self._eager_step(data, alpha)
+        if self._graph is None:
+            for pg in self.optimizer_G.param_groups + self.optimizer_D.param_groups:
+                pg["capturable"] = True  # before the first step: Adam's step counters live on the device
+            if self._eager_steps < self.GRAPH_WARMUP:
+                self._eager_steps += 1
+                return self._eager_step(data, alpha)
+            self._capture(data, alpha)
+            if self._graph is None:  # capture failed: stay eager, loudly
+                return self._eager_step(data, alpha)
+        self._load_static(data)
+        self._graph.replay()
+
+    def _capture(self, data, alpha):
+        from . import _lib
+        self._static_in = {k: torch.empty_like(v, device="cuda") for k, v in data.items() if torch.is_tensor(v)}
+        static = dict(data)
+        static.update(self._static_in)
+        self._load_static(data)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
+        try:
+            with torch.cuda.graph(graph):
+                self._eager_step(static, alpha)
+        except Exception as e:  # noqa: BLE001 -- an op that cannot be captured: report it and keep training eagerly
+            self.graph_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+            print("cocosnet_b200: CUDA-graph capture of the train step failed (%s); running eagerly" % self.graph_error)
+            torch.cuda.synchronize()
+            self._static_in = None
+            return
+        self.graph_native_launches = _lib.LAUNCHES - l0
+        self._graph = graph
 
     def run_generator_one_step(self, data, alpha=1):
         self.optimizer_G.zero_grad(set_to_none=True)
@@ -165,3 +228,4 @@ class Pix2PixTrainer:
                 pg["lr"] = g_lr
             print("update learning rate: %f -> %f" % (self.old_lr, new_lr))
             self.old_lr = new_lr
+            self._graph = None  # the learning rate is a launch constant of the captured fused-Adam kernels

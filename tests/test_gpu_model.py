@@ -107,3 +107,40 @@ def test_inference_mode_runs_and_is_deterministic():
     assert o1["fake_image"].shape == (2, 3, 256, 256) and o1["warp_out"].shape == (2, 3, 256, 256)
     assert torch.equal(o1["fake_image"], o2["fake_image"])
     assert torch.isfinite(o1["fake_image"]).all()
+
+
+@pytest.mark.timeout(900)
+def test_graphed_train_step_tracks_eager():
+    """trainer.run_step: eager for GRAPH_WARMUP calls, then ONE CUDA graph per iteration.  Same seed, same batches:
+    the losses after 6 iterations agree with a trainer that never captures (split-K atomics and cuDNN algorithm
+    choices make the two runs differ in the last bits, hence a tolerance, not equality)."""
+    from cocosnet_b200 import data as cdata
+    from cocosnet_b200.options import TrainOptions
+    from cocosnet_b200.trainer import Pix2PixTrainer
+    from oracle import torch_port
+
+    def run(use_graph):
+        opt = TrainOptions().parse(ADE_TRAIN[:-1] + ["2", "--gpu_ids", "0"], save=False, verbose=False)
+        opt.verbose_networks = False
+        opt.allow_random_vgg = True
+        torch.manual_seed(0)
+        trainer = Pix2PixTrainer(opt)
+        trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+        if not use_graph:
+            trainer.graph_error = "disabled for the comparison"
+        hist = []
+        for it in range(6):
+            batch = cdata.synthetic_batch(opt, 2, seed=100 + it)
+            trainer.run_step(batch)
+            hist.append({k: float(v.mean()) for k, v in trainer.get_latest_losses().items()})
+        return trainer, hist
+
+    tg, hg = run(True)
+    assert tg._graph is not None, tg.graph_error
+    assert tg.graph_native_launches > 100
+    te, he = run(False)
+    assert te._graph is None
+    for k in he[-1]:
+        assert abs(hg[-1][k] - he[-1][k]) <= 2e-2 * max(abs(he[-1][k]), 1e-2), (k, hg[-1][k], he[-1][k])
+    # the graph really trains: losses move between replays and the weights differ from the start
+    assert any(abs(hg[-1][k] - hg[-2][k]) > 0 for k in hg[-1])

@@ -35,9 +35,12 @@ def main():
         for i, data_i in enumerate(dataloader):
             p = min(float(i + (epoch - 1) * len(dataloader)) / 50 / len(dataloader), 1)
             alpha = 2.0 / (1.0 + np.exp(-10 * p)) - 1
-            if i % opt.D_steps_per_G == 0:
-                trainer.run_generator_one_step(data_i, alpha=alpha)
-            trainer.run_discriminator_one_step(data_i)
+            if opt.D_steps_per_G == 1 and not (opt.weight_domainC > 0 and opt.domain_rela):
+                trainer.run_step(data_i, alpha=alpha)  # alpha unused here; one GPU: CUDA-graph replay
+            else:
+                if i % opt.D_steps_per_G == 0:
+                    trainer.run_generator_one_step(data_i, alpha=alpha)
+                trainer.run_discriminator_one_step(data_i)
             steps += opt.batchSize
             if steps % opt.print_freq < opt.batchSize and int(os.environ.get("RANK", "0")) == 0:
                 print_current_errors(opt, epoch, i, trainer.get_latest_losses(), 0.0)
