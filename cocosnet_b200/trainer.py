@@ -162,6 +162,9 @@ class Pix2PixTrainer:
         except Exception as e:  # noqa: BLE001 -- an op that cannot be captured: report it and keep training eagerly
             self.graph_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
             print("cocosnet_b200: CUDA-graph capture of the train step failed (%s); running eagerly" % self.graph_error)
+            if os.environ.get("COCOS_GRAPH_TRACE", "0") == "1":
+                import traceback
+                traceback.print_exc()
             torch.cuda.synchronize()
             self._static_in = None
             return

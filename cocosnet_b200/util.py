@@ -24,13 +24,19 @@ def mse_loss(inp, target=0):  # util/util.py:42-43
 _VGG_MEAN = (0.40760392, 0.45795686, 0.48501961)
 
 
+_VGG_MEAN_CACHE = {}
+
+
 def vgg_preprocess(t, vgg_normal_correct=False):
     """RGB in [0,1] (or [-1,1] with vgg_normal_correct) -> BGR, mean-subtracted,
     x255 (util/util.py:45-54)."""
     if vgg_normal_correct:
         t = (t + 1) / 2
     bgr = t.flip(1)
-    mean = torch.tensor(_VGG_MEAN, dtype=t.dtype, device=t.device).view(1, 3, 1, 1)
+    key = (t.dtype, t.device)
+    mean = _VGG_MEAN_CACHE.get(key)
+    if mean is None:  # built once per device: a host->device copy of a Python list cannot be captured in a CUDA graph
+        mean = _VGG_MEAN_CACHE[key] = torch.tensor(_VGG_MEAN, dtype=t.dtype, device=t.device).view(1, 3, 1, 1)
     return (bgr - mean) * 255
 
 
