@@ -239,6 +239,19 @@ def main():
             step_resident()
     for _ in range(warmup):
         step_resident()
+    if trainer.graph_error is not None:  # never time a trainer that went through a failed capture: start over, eagerly
+        import gc
+        err = trainer.graph_error
+        del trainer
+        gc.collect()
+        torch.cuda.empty_cache()
+        os.environ["COCOS_CUDA_GRAPH"] = "0"
+        torch.manual_seed(0)
+        trainer = Pix2PixTrainer(opt)
+        trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+        trainer.graph_error = err
+        for _ in range(warmup):
+            step_resident()
     graphed = trainer._graph is not None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = _lib.LAUNCHES

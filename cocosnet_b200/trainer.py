@@ -153,6 +153,14 @@ class Pix2PixTrainer:
         static = dict(data)
         static.update(self._static_in)
         self._load_static(data)
+        # The eager iterations ran on the default stream and their autograd graphs (kept alive by the loss / output
+        # dicts) pin every parameter's AccumulateGrad node to that stream; a backward captured on the side stream
+        # would then have to synchronise with the legacy stream, which invalidates the capture.  Drop them first.
+        import gc
+        self.g_losses, self.d_losses, self.out = {}, {}, {}
+        self.optimizer_G.zero_grad(set_to_none=True)
+        self.optimizer_D.zero_grad(set_to_none=True)
+        gc.collect()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         l0 = _lib.LAUNCHES
