@@ -108,7 +108,7 @@ class Pix2PixTrainer:
             self._g_params = [p for k in ("netG", "netCorr") for p in net[k].parameters()]
             self._d_params = [p for p in net["netD"].parameters()]
         self.g_losses, self.d_losses, self.out = {}, {}, {}
-        self._graph, self._static_in, self._eager_steps = None, None, 0
+        self._graph, self._static_in, self._eager_steps, self._side = None, None, 0, None
         self.graph_native_launches = 0
         self.graph_error = None
 
@@ -117,7 +117,7 @@ class Pix2PixTrainer:
 
     def graph_capable(self):
         return (self.opt.isTrain and len(self.opt.gpu_ids) > 0 and _world() == 1
-                and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
+                and os.environ.get("COCOS_CUDA_GRAPH", "0") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
         self.run_generator_one_step(data, alpha)
@@ -129,7 +129,7 @@ class Pix2PixTrainer:
 
     def run_step(self, data, alpha=1):
         """One full training iteration (== run_generator_one_step + run_discriminator_one_step, train.py:55-59).
-        Every call is exactly one optimiser step of G and of D.  On one GPU the first GRAPH_WARMUP calls run eagerly,
+        Every call is exactly one optimiser step of G and of D.  On one GPU (opt-in: COCOS_CUDA_GRAPH=1) the first GRAPH_WARMUP calls run eagerly,
         the next one captures the iteration into a CUDA graph, and from then on a call is: copy the batch into the
         static input buffers (host or device source) + one graph launch.  `alpha`, the learning rates and the batch
         shapes are baked into the graph (update_learning_rate drops it; it is re-captured on the next call)."""
@@ -139,8 +139,17 @@ class Pix2PixTrainer:
             for pg in self.optimizer_G.param_groups + self.optimizer_D.param_groups:
                 pg["capturable"] = True  # before the first step: Adam's step counters live on the device
             if self._eager_steps < self.GRAPH_WARMUP:
+                # on a side stream: modules that keep a piece of the autograd graph between iterations (spectral
+                # norm's cached `weight`) keep the parameters' AccumulateGrad nodes alive, and a node born on the
+                # legacy default stream cannot be used from a capturing stream
                 self._eager_steps += 1
-                return self._eager_step(data, alpha)
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self._eager_step(data, alpha)
+                torch.cuda.current_stream().wait_stream(self._side)
+                return None
             self._capture(data, alpha)
             if self._graph is None:  # capture failed: stay eager, loudly
                 return self._eager_step(data, alpha)
