@@ -380,7 +380,7 @@ def test_conv_wgrad_rejects_narrow_layers():
 
 
 @pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", CONV_CASES)
-def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_padded):
+def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_padded, monkeypatch):
     """K2 forward (tcgen05 implicit GEMM, fp16 operands) vs torch conv2d in fp64; backward-data on the same kernel
     (bf16 operands: 2^-9 relative rounding on dy and W -> ~2e-3 rel-L2), weight/bias gradients through cuDNN."""
     import torch.nn.functional as F
@@ -392,6 +392,8 @@ def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_pad
     pad = ks // 2
     xin = F.pad(x, (pad, pad, pad, pad), mode="reflect") if (pre_padded and pad) else x
     xin = xin.clone().requires_grad_(True)
+    monkeypatch.setattr(ops, "NATIVE_DGRAD", True)
+    monkeypatch.setattr(ops, "NATIVE_WGRAD", True)
     y = ops.conv_native(xin, wgt, bias, pre_padded=pre_padded)
     ref = F.conv2d(xin.detach().double(), wgt.detach().double(), bias.detach().double(), padding=0 if pre_padded else pad)
     assert y.shape == ref.shape

@@ -53,9 +53,9 @@ def test_train_step_matches_reference_golden(config, native_conv):
     from cocosnet_b200 import data as cdata, ops
     gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
     old = torch.backends.cudnn.allow_tf32
-    old_native = ops.NATIVE_CONV
+    old_native, old_dgrad = ops.NATIVE_CONV, ops.NATIVE_DGRAD
     torch.backends.cudnn.allow_tf32 = False  # strict numerics for the parity check
-    ops.NATIVE_CONV = native_conv
+    ops.NATIVE_CONV = ops.NATIVE_DGRAD = native_conv  # native: forward, backward-data and backward-weights on K2
     tol = 5.0 if native_conv else 1.0
     try:
         opt, model = _build(gpu=True, config=config)
@@ -65,7 +65,7 @@ def test_train_step_matches_reference_golden(config, native_conv):
         d_losses = model(batch, mode="discriminator", GforD={"fake_image": out["fake_image"]})
     finally:
         torch.backends.cudnn.allow_tf32 = old
-        ops.NATIVE_CONV = old_native
+        ops.NATIVE_CONV, ops.NATIVE_DGRAD = old_native, old_dgrad
     # outputs: north-star tolerance 1e-3 relative
     # (TF32-class conv rounding upstream of the correlation is amplified by 1/temperature = 100: measured
     #  3e-3..6e-3 on warp_out for cuDNN-TF32 and for the native kernels alike, profiles/r01_precision_modes.txt)
