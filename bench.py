@@ -239,19 +239,13 @@ def main():
             step_resident()
     for _ in range(warmup):
         step_resident()
-    if trainer.graph_error is not None:  # never time a trainer that went through a failed capture: start over, eagerly
-        import gc
-        err = trainer.graph_error
-        del trainer
-        gc.collect()
-        torch.cuda.empty_cache()
+    if trainer.graph_error is not None:
+        # never time a process that went through a failed capture (allocator pools and the RNG's capture state are
+        # not trustworthy afterwards): start over in a fresh interpreter, eagerly.  Only reachable with one GPU.
+        sys.stderr.write("bench: CUDA-graph capture failed (%s); re-running eagerly\n" % trainer.graph_error)
+        sys.stderr.flush()
         os.environ["COCOS_CUDA_GRAPH"] = "0"
-        torch.manual_seed(0)
-        trainer = Pix2PixTrainer(opt)
-        trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
-        trainer.graph_error = err
-        for _ in range(warmup):
-            step_resident()
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     graphed = trainer._graph is not None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = _lib.LAUNCHES

@@ -315,8 +315,8 @@ def conv_wgrad_native(dy, x, ks, pre_padded):
 NATIVE_WGRAD = _os.environ.get("COCOS_NATIVE_WGRAD", "1") == "1"
 # backward-data on K2 costs one more transpose-pack + weight re-layout per layer: measured on the eager ade20k step
 # (launch-bound, profiles/README.md) 179 ms with it vs 170.5 ms without, although the GPU-busy time is lower with it
-# (160 vs 163 ms) -- so it is the default only when the step is replayed from a CUDA graph.
-NATIVE_DGRAD = _os.environ.get("COCOS_NATIVE_DGRAD", _os.environ.get("COCOS_CUDA_GRAPH", "0")) == "1"
+# (160 vs 163 ms) -- so Pix2PixTrainer turns it on exactly when the iteration is replayed from a CUDA graph.
+NATIVE_DGRAD = _os.environ.get("COCOS_NATIVE_DGRAD", "0") == "1"
 
 
 class _ConvNative(torch.autograd.Function):

@@ -109,6 +109,11 @@ class Pix2PixTrainer:
             self._d_params = [p for p in net["netD"].parameters()]
         self.g_losses, self.d_losses, self.out = {}, {}, {}
         self._graph, self._static_in, self._eager_steps, self._side = None, None, 0, None
+        if opt.isTrain and "COCOS_NATIVE_DGRAD" not in os.environ:
+            # K2 backward-data lowers the GPU-busy time but adds launches: it pays off once the iteration is replayed
+            # from a graph and costs 5 % on the launch-bound eager step (profiles/README.md, r01 A/B)
+            from . import ops
+            ops.NATIVE_DGRAD = self.graph_capable()
         self.graph_native_launches = 0
         self.graph_error = None
 
@@ -117,7 +122,7 @@ class Pix2PixTrainer:
 
     def graph_capable(self):
         return (self.opt.isTrain and len(self.opt.gpu_ids) > 0 and _world() == 1
-                and os.environ.get("COCOS_CUDA_GRAPH", "0") == "1" and self.graph_error is None)
+                and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
         self.run_generator_one_step(data, alpha)
@@ -129,7 +134,7 @@ class Pix2PixTrainer:
 
     def run_step(self, data, alpha=1):
         """One full training iteration (== run_generator_one_step + run_discriminator_one_step, train.py:55-59).
-        Every call is exactly one optimiser step of G and of D.  On one GPU (opt-in: COCOS_CUDA_GRAPH=1) the first GRAPH_WARMUP calls run eagerly,
+        Every call is exactly one optimiser step of G and of D.  On one GPU (COCOS_CUDA_GRAPH=0 turns it off) the first GRAPH_WARMUP calls run eagerly,
         the next one captures the iteration into a CUDA graph, and from then on a call is: copy the batch into the
         static input buffers (host or device source) + one graph launch.  `alpha`, the learning rates and the batch
         shapes are baked into the graph (update_learning_rate drops it; it is re-captured on the next call)."""
