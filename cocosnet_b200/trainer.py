@@ -109,13 +109,13 @@ class Pix2PixTrainer:
             self._d_params = [p for p in net["netD"].parameters()]
         self.g_losses, self.d_losses, self.out = {}, {}, {}
         self._graph, self._static_in, self._eager_steps, self._side = None, None, 0, None
+        self.graph_native_launches = 0
+        self.graph_error = None
         if opt.isTrain and "COCOS_NATIVE_DGRAD" not in os.environ:
             # K2 backward-data lowers the GPU-busy time but adds launches: it pays off once the iteration is replayed
             # from a graph and costs 5 % on the launch-bound eager step (profiles/README.md, r01 A/B)
             from . import ops
             ops.NATIVE_DGRAD = self.graph_capable()
-        self.graph_native_launches = 0
-        self.graph_error = None
 
     # ------------------------------------------------------------------ CUDA-graph step (one GPU)
     GRAPH_WARMUP = 3  # eager iterations before the capture (cuDNN autotuning, lazy state, allocator warm-up)
