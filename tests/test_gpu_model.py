@@ -150,7 +150,7 @@ def test_graphed_train_step_tracks_eager(monkeypatch):
     # reconstruction losses still agree while the adversarial ones have diverged chaotically (batch 2, random data).
     for k in he[3]:
         tol = 0.5 if k == "mask" else 3e-2
-        assert abs(hg[3][k] - he[3][k]) <= tol * max(abs(he[3][k]), 0.1), (3, k, hg[3][k], he[3][k])
+        assert abs(hg[3][k] - he[3][k]) <= tol * max(abs(he[3][k]), 1.0), (3, k, hg[3][k], he[3][k])
     for k in ("perc", "contextual", "fm"):
         assert abs(hg[5][k] - he[5][k]) <= 3e-2 * abs(he[5][k]), (5, k, hg[5][k], he[5][k])
     # the graph really trains: losses move between replays and the weights differ from the start
