@@ -158,6 +158,8 @@ class Pix2PixTrainer:
             self._capture(data, alpha)
             if self._graph is None:  # capture failed: stay eager, loudly
                 return self._eager_step(data, alpha)
+        if any(tuple(data[k].shape) != tuple(buf.shape) for k, buf in self._static_in.items()):
+            return self._eager_step(data, alpha)  # e.g. the short last batch of an epoch: not the captured shapes
         self._load_static(data)
         self._graph.replay()
 
