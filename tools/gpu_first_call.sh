@@ -1,0 +1,23 @@
+#!/bin/bash
+# One gpurun call that answers the open questions of the previous round (run from the repo root on the GPU box):
+#   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+# Everything lands under gpurun_out/next/.
+set -u
+out=gpurun_out/next
+mkdir -p $out
+# 1. parity: whole GPU suite, then the experimental K2w flat mode on its own (a failure there must not hide the rest)
+python -m pytest tests -q -m gpu 2>&1 | tail -8 > $out/pytest_gpu.log
+COCOS_WGRAD_NARROW=1 timeout 300 python -m pytest tests/test_gpu_corr.py -q -m gpu -k "flat_mode" 2>&1 | tail -8 > $out/pytest_flat_mode.log
+# 2. the bench line (default path) and the eager one
+python bench.py 2>&1 | tail -1 > $out/bench_default.json
+COCOS_CUDA_GRAPH=0 python bench.py --no-cpu-baseline 2>&1 | tail -1 > $out/bench_eager.json
+# 3. is the flat-mode K2w worth routing?  (only meaningful if pytest_flat_mode.log is green)
+COCOS_WGRAD_NARROW=1 python bench.py --no-cpu-baseline 2>&1 | tail -1 > $out/bench_wgrad_narrow.json
+# 4. where the iteration spends its GPU time now (eager, per-op table; "GPU busy" double counts: halve it)
+COCOS_CUDA_GRAPH=0 python tools/profile_step.py --b 8 --cudnn_benchmark --rows 70 > $out/profile_step_table.txt 2>&1
+# 5. launch list of the default bench command for profiles/ (graph replay: kernels are still listed one by one)
+BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv \
+    --log-file $out/launches.csv python bench.py --steps 1 --warmup 1 > $out/bench_under_ncu.log 2>&1
+python tools/ncu_launch_summary.py $out/launches.csv > $out/launches_summary.txt 2>&1
+tail -3 $out/pytest_gpu.log $out/pytest_flat_mode.log
+cut -c1-300 $out/bench_default.json
