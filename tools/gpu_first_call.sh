@@ -15,9 +15,11 @@ COCOS_CUDA_GRAPH=0 python bench.py --no-cpu-baseline 2>&1 | tail -1 > $out/bench
 COCOS_WGRAD_NARROW=1 python bench.py --no-cpu-baseline 2>&1 | tail -1 > $out/bench_wgrad_narrow.json
 # 4. where the iteration spends its GPU time now (eager, per-op table; "GPU busy" double counts: halve it)
 COCOS_CUDA_GRAPH=0 python tools/profile_step.py --b 8 --cudnn_benchmark --rows 70 > $out/profile_step_table.txt 2>&1
-# 5. launch list of the default bench command for profiles/ (graph replay: kernels are still listed one by one)
-BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv \
-    --log-file $out/launches.csv python bench.py --steps 1 --warmup 1 > $out/bench_under_ncu.log 2>&1
-python tools/ncu_launch_summary.py $out/launches.csv > $out/launches_summary.txt 2>&1
+# 5. (opt-in: `bash tools/gpu_first_call.sh ncu`; the last one cost 19 GPU-minutes) launch list of the eager bench
+if [ "${1:-}" = "ncu" ]; then
+  COCOS_CUDA_GRAPH=0 BENCH_PROFILE=1 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv \
+      --log-file $out/launches.csv python bench.py --steps 1 --warmup 1 > $out/bench_under_ncu.log 2>&1
+  python tools/ncu_launch_summary.py $out/launches.csv > $out/launches_summary.txt 2>&1
+fi
 tail -3 $out/pytest_gpu.log $out/pytest_flat_mode.log
 cut -c1-300 $out/bench_default.json
