@@ -200,8 +200,7 @@ def main():
     trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
     # weak scaling: every rank owns a distinct batch of 8 (global batch = 8 * N); the trainer's
     # shard_batch() is bypassed by handing it the rank-local shard directly
-    import cocosnet_b200.trainer as tr
-    tr.shard_batch = lambda d, rank=None, world=None: d
+    trainer.pre_sharded = True
     host = cdata.synthetic_batch(opt, PER_GPU_BATCH, seed=1234 + 1000 * rank, pin=True)
     dev = {k: (v.cuda(non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))

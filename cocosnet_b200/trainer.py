@@ -111,6 +111,7 @@ class Pix2PixTrainer:
         self._graph, self._static_in, self._eager_steps, self._side = None, None, 0, None
         self.graph_native_launches = 0
         self.graph_error = None
+        self.pre_sharded = bool(getattr(opt, "pre_sharded", False))
         if opt.isTrain and "COCOS_NATIVE_DGRAD" not in os.environ:
             # K2 backward-data lowers the GPU-busy time but adds launches: it pays off once the iteration is replayed
             # from a graph and costs 5 % on the launch-bound eager step (profiles/README.md, r01 A/B)
@@ -195,6 +196,11 @@ class Pix2PixTrainer:
         self.graph_native_launches = _lib.LAUNCHES - l0
         self._graph = graph
 
+    def _shard(self, data):
+        """This rank's slice of a global batch; `pre_sharded` = the caller already hands over rank-local batches
+        (a per-rank data loader, bench.py's weak-scaling batches)."""
+        return data if self.pre_sharded else shard_batch(data)
+
     def run_generator_one_step(self, data, alpha=1):
         self.optimizer_G.zero_grad(set_to_none=True)
         # The G step only needs the gradient THROUGH the discriminator, not its weight gradients (the reference
@@ -202,7 +208,7 @@ class Pix2PixTrainer:
         for p in self._d_params:
             p.requires_grad_(False)
         try:
-            g_losses, out = self.pix2pix_model(shard_batch(data), mode="generator", alpha=alpha)
+            g_losses, out = self.pix2pix_model(self._shard(data), mode="generator", alpha=alpha)
             g_loss = sum(g_losses.values()).mean()
             g_loss.backward()
         finally:
@@ -218,7 +224,7 @@ class Pix2PixTrainer:
     def run_discriminator_one_step(self, data):
         self.optimizer_D.zero_grad(set_to_none=True)
         GforD = {k: self.out.get(k) for k in ("fake_image", "adaptive_feature_seg", "adaptive_feature_img")}
-        d_losses = self.pix2pix_model(shard_batch(data), mode="discriminator", GforD=GforD)
+        d_losses = self.pix2pix_model(self._shard(data), mode="discriminator", GforD=GforD)
         d_loss = sum(d_losses.values()).mean()
         d_loss.backward()
         allreduce_grads(self._d_params)
