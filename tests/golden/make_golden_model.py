@@ -78,11 +78,46 @@ def run(name):
     print(os.path.getsize(path) // 1024, "KiB")
 
 
+INFER_CONFIGS = {
+    # BASELINE.json configs[0]: the reference's CPU-runnable numerics case -- ade20k inference flags at batch 1, with the
+    # default match_kernel 3 (K = 2304) and with match_kernel 1 (K = 256, the shape the kernel metric is quoted on)
+    "ade20k_infer_mk3": ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+                         "--batchSize", "1"],
+    "ade20k_infer_mk1": ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+                         "--match_kernel", "1", "--batchSize", "1"],
+}
+
+
+def run_inference(name):
+    """Seeded init (no checkpoint exists offline), modules in eval(), `mode='inference'` (pix2pix_model.py:74-86,
+    319-334): what test.py computes per batch."""
+    argv = INFER_CONFIGS[name]
+    batch = synthetic_batch_for(_opt_stub(argv), 1)
+    with rh.reference_imported(), rh.patched_for_cpu_training():
+        opt = rh.make_opt(argv, True)
+        from models.pix2pix_model import Pix2PixModel
+        torch.manual_seed(0)
+        model = Pix2PixModel(opt)
+        model.eval()
+        opt.isTrain = False  # constructed as a training model for the seeded init; forward as test.py would
+        opt.show_corr = False  # TestOptions default (test_options.py), read by correspondence.py:325
+        d = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        d["label"] = d["label"].long()
+        d["label_ref"] = d["label_ref"].long()
+        with torch.no_grad():
+            out = model(d, mode="inference")
+        res = {"fake_image_sub": out["fake_image"].numpy()[:, :, ::4, ::4],
+               "warp_out_sub": out["warp_out"].numpy()[:, :, ::4, ::4]}
+    path = os.path.join(HERE, "model_%s.npz" % name)
+    np.savez_compressed(path, **res)
+    print(name, {k: v.shape for k, v in res.items()}, os.path.getsize(path) // 1024, "KiB")
+
+
 def _opt_stub(argv):
     from cocosnet_b200.options import TrainOptions
     return TrainOptions().parse(list(argv) + ["--gpu_ids", "-1"], save=False, verbose=False)
 
 
 if __name__ == "__main__":
-    for n in sys.argv[1:] or list(CONFIGS):
-        run(n)
+    for n in sys.argv[1:] or (list(CONFIGS) + list(INFER_CONFIGS)):
+        run_inference(n) if n in INFER_CONFIGS else run(n)

@@ -88,3 +88,42 @@ def test_full_train_step_matches_reference_golden(config):
             _, netk, pname = key.split("_", 2)
             p = dict(model.net[netk].named_parameters())[pname]
             assert abs(float(p.grad.norm()) - float(gold[key][0])) <= 2e-3 * float(gold[key][0]), key
+
+
+INFER_CONFIGS = {
+    "ade20k_infer_mk3": ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+                         "--batchSize", "1", "--gpu_ids", "-1"],
+    "ade20k_infer_mk1": ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+                         "--match_kernel", "1", "--batchSize", "1", "--gpu_ids", "-1"],
+}
+
+
+def build_inference_model(config, gpu=False):
+    """Seeded training-mode construction (bit-identical init, no checkpoint offline), then eval() + isTrain=False:
+    what the golden script does to the reference (tests/golden/make_golden_model.py:run_inference)."""
+    from cocosnet_b200.pix2pix_model import Pix2PixModel
+    opt = TrainOptions().parse(INFER_CONFIGS[config], save=False, verbose=False)
+    opt.verbose_networks = False
+    opt.allow_random_vgg = True
+    torch.manual_seed(0)
+    model = Pix2PixModel(opt)
+    model.eval()
+    opt.isTrain = False
+    opt.show_corr = False
+    if gpu:
+        opt.gpu_ids = [0]
+        model.cuda()
+    return opt, model
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("config", list(INFER_CONFIGS))
+def test_inference_matches_reference_golden(config):
+    """BASELINE configs[0] (the reference's CPU-runnable case): `mode='inference'` of the host mirror on CPU."""
+    gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
+    opt, model = build_inference_model(config)
+    batch = cdata.synthetic_batch(opt, 1)
+    with torch_port.cpu_reference_mode(), torch.no_grad():
+        out = model(batch, mode="inference")
+    assert np.allclose(out["warp_out"].numpy()[:, :, ::4, ::4], gold["warp_out_sub"], atol=2e-5)
+    assert np.allclose(out["fake_image"].numpy()[:, :, ::4, ::4], gold["fake_image_sub"], atol=2e-5)
