@@ -1,6 +1,7 @@
 """Stage-by-stage GPU bring-up diagnostics (each stage in its own process so a
 trapped kernel does not poison the next).  Usage: python tools/gpu_bringup.py [stage ...]
-Not a test: prints numbers that localise descriptor / pipeline bugs."""
+Not a pytest test, but test infrastructure all the same: it uses the CPU oracle as the checker and prints numbers
+that localise descriptor / pipeline bugs."""
 import os
 import subprocess
 import sys

@@ -10,7 +10,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from cocosnet_b200 import data as cdata  # noqa: E402
 from cocosnet_b200.trainer import Pix2PixTrainer  # noqa: E402
-from oracle import torch_port  # noqa: E402
 
 
 def main():
@@ -26,7 +25,6 @@ def main():
     opt.channels_last = args.channels_last
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
-    trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
     batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cdata.synthetic_batch(opt, args.b).items()}
 
     def step():
