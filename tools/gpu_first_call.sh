@@ -20,6 +20,11 @@ if [ "${1:-}" = "ncu" ]; then
   COCOS_CUDA_GRAPH=0 BENCH_PROFILE=1 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv \
       --log-file $out/launches.csv python bench.py --steps 1 --warmup 1 > $out/bench_under_ncu.log 2>&1
   python tools/ncu_launch_summary.py $out/launches.csv > $out/launches_summary.txt 2>&1
+  # one full capture each of K2 forward and K2w (none exists yet): tensor-pipe share, DRAM bytes vs algorithmic
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_fwd_kernel -s 3 -c 1 \
+      -o $out/k2_fwd python tools/bench_conv.py > $out/ncu_k2_fwd.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_kernel -s 1 -c 1 \
+      -o $out/k2_wgrad python tools/debug_wgrad.py 8 512 512 64 64 3 1 1 > $out/ncu_k2_wgrad.log 2>&1
 fi
 tail -3 $out/pytest_gpu.log $out/pytest_flat_mode.log
 cut -c1-300 $out/bench_default.json
