@@ -29,6 +29,22 @@ SIGNATURES = {
     "cocos_normalize_pack": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp],
     "cocos_inst_act_fwd": [_vp] * 4 + [_c_int, _c_int, _c_float, _c_float, _vp],
     "cocos_inst_act_bwd": [_vp] * 5 + [_c_int, _c_int, _c_float, _vp],
+    "cocos_tapconv": [_vp, _vp],
+    "cocos_tapwgrad": [_vp, _vp],
+    "cocos_pack_w": [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _c_int, _vp],
+    "cocos_spade_mod_nhwc_fwd": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp] + [_c_int] * 5
+                                + [_c_float, _c_float, _vp],
+    "cocos_spade_mod_nhwc_bwd": [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _c_int,
+                                 _vp, _c_int] + [_c_int] * 5 + [_c_float, _vp],
+    "cocos_in_stats_nhwc": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "cocos_inst_act_nhwc_fwd": [_vp, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp, _c_float, _vp, _c_int, _c_int,
+                                _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp],
+    "cocos_inst_act_nhwc_bwd": [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp,
+                                _c_float, _vp, _vp, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                _c_int, _c_float, _vp],
+    "cocos_nhwc_pack": [_vp, _vp] + [_c_int] * 11 + [_vp],
+    "cocos_nhwc_unpack": [_vp] + [_c_int] * 8 + [_vp] + [_c_int] * 6 + [_vp],
+    "cocos_colsum_nhwc": [_vp, _c_int, _c_int, _c_int, _c_ll, _vp, _vp],
     "cocos_gemm_f16": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
                        _c_float, _c_int, _c_int, _vp],
 }

@@ -139,4 +139,103 @@ int cocos_conv_fwd(const void* x, const void* wt, const float* bias, float* y, i
                          static_cast<cudaStream_t>(stream));
 }
 
+int cocos_tapconv(const cocos_tapconv_desc* desc, void* stream) {
+  return tapconv_launch(desc, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_tapwgrad(const cocos_tapwgrad_desc* desc, void* stream) {
+  return tapwgrad_launch(desc, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_pack_w(const float* w, int Cout, int Cin, int KS, void* dst, int rows, int rows_alloc, int Kc, int ngroups,
+                 const signed char* r, const signed char* s, const signed char* term, int transposed, int bf16,
+                 void* stream) {
+  return pack_w_launch(w, Cout, Cin, KS, dst, rows, rows_alloc, Kc, ngroups, r, s, term, transposed, bf16,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
+                             int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
+                             float slope, float eps, void* stream) {
+  if (!x || !gb || !y || !mean || !rstd) {
+    set_error("cocos_spade_mod_nhwc_fwd: null pointer argument");
+    return -1;
+  }
+  return spade_mod_nhwc_fwd_launch(x, x_kind, x_Cs, gb, gb_kind, gb_Cs, y, y_Cs, y_lo_off, mean, rstd, B, C, H, W, pad,
+                                   slope, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
+                             int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
+                             int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
+                             void* stream) {
+  if (!dy || !x || !gb || !mean || !rstd || !dx || !dgb) {
+    set_error("cocos_spade_mod_nhwc_bwd: null pointer argument");
+    return -1;
+  }
+  return spade_mod_nhwc_bwd_launch(dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, mean, rstd, dx, dx_Cs, dx_acc, dgb,
+                                   dgb_Cs, B, C, H, W, pad, slope, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_in_stats_nhwc(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, void* stream) {
+  if (!x || !stats) {
+    set_error("cocos_in_stats_nhwc: null pointer argument");
+    return -1;
+  }
+  return in_stats_nhwc_launch(x, kind, Cs, B, C, HW, stats, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_inst_act_nhwc_fwd(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
+                            int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
+                            int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
+                            void* stream) {
+  if (!x || !stats || !y) {
+    set_error("cocos_inst_act_nhwc_fwd: null pointer argument");
+    return -1;
+  }
+  return inst_act_nhwc_fwd_launch(x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, y, y_kind, y_Cs,
+                                  y_lo_off, y_pad, y2, y2_Cs, B, C, H, W, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
+                            int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
+                            const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
+                            int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
+                            void* stream) {
+  if (!dy || !x || !stats || !dx) {
+    set_error("cocos_inst_act_nhwc_bwd: null pointer argument");
+    return -1;
+  }
+  return inst_act_nhwc_bwd_launch(dy, dy_Cs, dy_pad, dy2, dy2_Cs, x, x_kind, x_Cs, stats, res, res_kind, res_Cs,
+                                  slope_ptr, slope, bstats, dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C,
+                                  H, W, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
+                    int W, int f, int pad, void* stream) {
+  if (!src || !dst) {
+    set_error("cocos_nhwc_pack: null pointer argument");
+    return -1;
+  }
+  return nhwc_pack_launch(src, dst, kind, B, C, Cs, lo_off, Hs, Ws, H, W, f, pad, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_nhwc_unpack(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,
+                      int Cd, int cd_lo, int Hd, int Wd, int f, int acc, void* stream) {
+  if (!src || !dst) {
+    set_error("cocos_nhwc_unpack: null pointer argument");
+    return -1;
+  }
+  return nhwc_unpack_launch(src, kind, Cs, c_lo, C, B, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f, acc,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cocos_colsum_nhwc(const void* x, int kind, int Cs, int C, long long rows, float* out, void* stream) {
+  if (!x || !out) {
+    set_error("cocos_colsum_nhwc: null pointer argument");
+    return -1;
+  }
+  return colsum_nhwc_launch(x, kind, Cs, C, rows, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

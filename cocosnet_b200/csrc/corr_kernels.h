@@ -62,3 +62,37 @@ int spade_mod_bwd_launch(const float* dy, const float* x, const float* gb, const
                          cudaStream_t stream);
 
 }  // namespace cocos
+
+struct cocos_tapconv_desc;
+struct cocos_tapwgrad_desc;
+namespace cocos {
+// 16-bit NHWC pipeline (tapconv.cu, tapwgrad.cu, ew_nhwc.cu)
+int tapconv_launch(const cocos_tapconv_desc* d, cudaStream_t stream);
+void tapconv_tile_shape(int B, int H, int W, int* TB, int* TH, int* TW);
+int tapwgrad_launch(const cocos_tapwgrad_desc* d, cudaStream_t stream);
+int spade_mod_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
+                              int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
+                              float slope, float eps, cudaStream_t stream);
+int spade_mod_nhwc_bwd_launch(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
+                              int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
+                              int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
+                              cudaStream_t stream);
+int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, cudaStream_t stream);
+int inst_act_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
+                             int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
+                             int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
+                             cudaStream_t stream);
+int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
+                             int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
+                             const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
+                             int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
+                             cudaStream_t stream);
+int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
+                     int W, int f, int pad, cudaStream_t stream);
+int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,
+                       int Cd, int cd_lo, int Hd, int Wd, int f, int acc, cudaStream_t stream);
+int colsum_nhwc_launch(const void* x, int kind, int Cs, int C, long long rows, float* out, cudaStream_t stream);
+int pack_w_launch(const float* w, int Cout, int Cin, int KS, void* dst, int rows, int rows_alloc, int Kc, int ngroups,
+                  const signed char* r, const signed char* s, const signed char* term, int transposed, int bf16,
+                  cudaStream_t stream);
+}  // namespace cocos

@@ -1,0 +1,779 @@
+// HBM-bound elementwise / normalisation kernels of the 16-bit NHWC pipeline (everything between two tap
+// convolutions), sm_100a.  Tensor "kinds": 1 = fp16, 2 = bf16, 3 = fp32; activations NHWC [B, H, W, Cs] with channel
+// stride Cs >= C; gradients bf16.  `op` tensors (the A operand of the next convolution) are fp16, optionally carry
+// a 1-pixel reflection halo ([B, H+2, W+2, Cs]) and optionally a second fp16 term lo = x - fp16(x) at channel
+// offset lo_off (2-term split operands of the correspondence path).
+//
+//   spade_mod_nhwc   : PONO + SPADE modulation + LeakyReLU + ReflectionPad2d (normalization.py:63-68,149;
+//                      architecture.py:73-74,94-95) raw -> op, forward / backward
+//   in_stats_nhwc    : per-(image, channel) sum / sum of squares (InstanceNorm2d statistics)
+//   inst_act_nhwc    : InstanceNorm2d(affine=False) [+ residual] + LeakyReLU / PReLU [+ reflection halo]
+//                      (generator.py:104-113, discriminator.py:92-115, correspondence.py:13-36), forward / backward
+//   nhwc_pack        : fp32 NCHW -> op (nearest down-sampling by an integer factor, halo, split)
+//   nhwc_unpack      : NHWC (halo folded back) -> fp32 NCHW, overwrite or accumulate, strided scatter
+//   colsum_nhwc      : bias gradient  db[c] = sum over pixels
+//   pack_w           : fp32 [Cout, Cin, KS, KS] -> the K-major 16-bit weight matrix of a tap-group list
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/cocos_b200.h"
+#include "corr_kernels.h"
+#include "tmap.h"
+
+namespace cocos {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int reflect1(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// 4 consecutive channels starting at element index `idx` (multiple of 4)
+__device__ __forceinline__ float4 ld4(const void* base, int kind, size_t idx) {
+  if (kind == 3) return *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+  const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + idx);
+  if (kind == 1) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ void st4(void* base, int kind, size_t idx, float4 v) {
+  if (kind == 3) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx) = v;
+    return;
+  }
+  uint2 u;
+  if (kind == 1) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint2*>(static_cast<uint16_t*>(base) + idx) = u;
+}
+
+__device__ __forceinline__ float lo16(float v) { return v - __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float4 lo4(float4 v) { return make_float4(lo16(v.x), lo16(v.y), lo16(v.z), lo16(v.w)); }
+__device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+
+// ----------------------------------------------------------------------------------------------- SPADE modulation
+struct SpadeFwd {
+  const void* x; int x_kind, x_Cs;
+  const void* gb; int gb_kind, gb_Cs;   // gamma at channel [0,C), beta at [C,2C)
+  void* y; int y_Cs, y_lo_off;          // fp16 op, [B, H+2p, W+2p, y_Cs]
+  float* mean; float* rstd;             // [B,H,W]
+  int B, C, H, W, pad;
+  float slope, eps;
+};
+
+// one warp per (padded) output pixel
+__global__ void __launch_bounds__(256) spade_mod_nhwc_fwd_kernel(const SpadeFwd p) {
+  const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+  const int lane = threadIdx.x & 31;
+  const long long op = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (op >= static_cast<long long>(p.B) * Hp * Wp) return;
+  const int b = static_cast<int>(op / (Hp * Wp));
+  const int r = static_cast<int>(op - static_cast<long long>(b) * Hp * Wp);
+  const int ho = r / Wp, wo = r - ho * Wp;
+  const int hs = reflect1(ho - p.pad, p.H), ws = reflect1(wo - p.pad, p.W);
+  const size_t spix = (static_cast<size_t>(b) * p.H + hs) * p.W + ws;
+  const size_t xo = spix * p.x_Cs, go = spix * p.gb_Cs, yo = static_cast<size_t>(op) * p.y_Cs;
+  const int n4 = p.C >> 2;
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(sum) / p.C;
+  float ss = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
+    const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (p.C - 1) + p.eps);
+  if (lane == 0 && ho - p.pad == hs && wo - p.pad == ws) {
+    p.mean[spix] = mean;
+    p.rstd[spix] = rstd;
+  }
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
+    const float4 g = ld4(p.gb, p.gb_kind, go + 4 * i), be = ld4(p.gb, p.gb_kind, go + p.C + 4 * i);
+    float4 z;
+    z.x = lrelu(fmaf((v.x - mean) * rstd, 1.0f + g.x, be.x), p.slope);
+    z.y = lrelu(fmaf((v.y - mean) * rstd, 1.0f + g.y, be.y), p.slope);
+    z.z = lrelu(fmaf((v.z - mean) * rstd, 1.0f + g.z, be.z), p.slope);
+    z.w = lrelu(fmaf((v.w - mean) * rstd, 1.0f + g.w, be.w), p.slope);
+    st4(p.y, 1, yo + 4 * i, z);
+    if (p.y_lo_off) st4(p.y, 1, yo + p.y_lo_off + 4 * i, lo4(z));
+  }
+}
+
+struct SpadeBwd {
+  const void* dy; int dy_Cs;            // bf16 [B, H+2p, W+2p, dy_Cs]
+  const void* x; int x_kind, x_Cs;
+  const void* gb; int gb_kind, gb_Cs;
+  const float* mean; const float* rstd;
+  void* dx; int dx_Cs, dx_acc;          // bf16 [B,H,W,dx_Cs]; dx_acc: add to what is there
+  void* dgb; int dgb_Cs;                // bf16 [B,H,W,dgb_Cs]: d gamma [0,C), d beta [C,2C)
+  int B, C, H, W, pad;
+  float slope;
+};
+
+// gradient of the padded output folded back onto source pixel (h, w): up to 3 x 3 halo images
+struct Fold {
+  int hc[3], wc[3], nh, nw;
+};
+__device__ __forceinline__ Fold make_fold(int h, int w, int H, int W, int pad) {
+  Fold f;
+  f.nh = f.nw = 0;
+  f.hc[f.nh++] = h + pad;
+  f.wc[f.nw++] = w + pad;
+  if (pad) {
+    if (h >= 1 && h <= pad) f.hc[f.nh++] = pad - h;
+    if (h <= H - 2 && h >= H - 1 - pad) f.hc[f.nh++] = 2 * (H - 1) - h + pad;
+    if (w >= 1 && w <= pad) f.wc[f.nw++] = pad - w;
+    if (w <= W - 2 && w >= W - 1 - pad) f.wc[f.nw++] = 2 * (W - 1) - w + pad;
+  }
+  return f;
+}
+__device__ __forceinline__ float4 folded4(const void* dy, int kind, const Fold& f, size_t img_off, int Wp, int Cs,
+                                          int c) {
+  float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < f.nh; ++a)
+    for (int e = 0; e < f.nw; ++e) {
+      const float4 t = ld4(dy, kind, (img_off + static_cast<size_t>(f.hc[a]) * Wp + f.wc[e]) * Cs + c);
+      d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+    }
+  return d;
+}
+
+// one warp per source pixel; two passes over the channels (sums, then the outputs)
+__global__ void __launch_bounds__(256) spade_mod_nhwc_bwd_kernel(const SpadeBwd p) {
+  const int Hp = p.H + 2 * p.pad, Wp = p.W + 2 * p.pad;
+  const int lane = threadIdx.x & 31;
+  const long long pixl = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (pixl >= static_cast<long long>(p.B) * p.H * p.W) return;
+  const size_t spix = static_cast<size_t>(pixl);
+  const int b = static_cast<int>(pixl / (p.H * p.W));
+  const int r = static_cast<int>(pixl - static_cast<long long>(b) * p.H * p.W);
+  const int h = r / p.W, w = r - h * p.W;
+  const Fold f = make_fold(h, w, p.H, p.W, p.pad);
+  const size_t img = static_cast<size_t>(b) * Hp * Wp;
+  const size_t xo = spix * p.x_Cs, go = spix * p.gb_Cs;
+  const int n4 = p.C >> 2;
+  const float mean = p.mean[spix], rstd = p.rstd[spix];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    float4 d = folded4(p.dy, 2, f, img, Wp, p.dy_Cs, 4 * i);
+    const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
+    const float4 g = ld4(p.gb, p.gb_kind, go + 4 * i), be = ld4(p.gb, p.gb_kind, go + p.C + 4 * i);
+    const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd, xh2 = (v.z - mean) * rstd,
+                xh3 = (v.w - mean) * rstd;
+    d.x = fmaf(xh0, 1.0f + g.x, be.x) > 0.f ? d.x : d.x * p.slope;
+    d.y = fmaf(xh1, 1.0f + g.y, be.y) > 0.f ? d.y : d.y * p.slope;
+    d.z = fmaf(xh2, 1.0f + g.z, be.z) > 0.f ? d.z : d.z * p.slope;
+    d.w = fmaf(xh3, 1.0f + g.w, be.w) > 0.f ? d.w : d.w * p.slope;
+    st4(p.dgb, 2, spix * p.dgb_Cs + 4 * i, make_float4(d.x * xh0, d.y * xh1, d.z * xh2, d.w * xh3));
+    st4(p.dgb, 2, spix * p.dgb_Cs + p.C + 4 * i, d);
+    const float e0 = d.x * (1.0f + g.x), e1 = d.y * (1.0f + g.y), e2 = d.z * (1.0f + g.z), e3 = d.w * (1.0f + g.w);
+    s1 += (e0 + e1) + (e2 + e3);
+    s2 += (e0 * xh0 + e1 * xh1) + (e2 * xh2 + e3 * xh3);
+  }
+  const float m1 = warp_sum(s1) / p.C, m2 = warp_sum(s2) / (p.C - 1);
+  for (int i = lane; i < n4; i += 32) {
+    // d beta was just written by this lane: dz = d beta, no need to fold again
+    const float4 d = ld4(p.dgb, 2, spix * p.dgb_Cs + p.C + 4 * i);
+    const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
+    const float4 g = ld4(p.gb, p.gb_kind, go + 4 * i);
+    float4 t;
+    t.x = rstd * (d.x * (1.0f + g.x) - m1 - (v.x - mean) * rstd * m2);
+    t.y = rstd * (d.y * (1.0f + g.y) - m1 - (v.y - mean) * rstd * m2);
+    t.z = rstd * (d.z * (1.0f + g.z) - m1 - (v.z - mean) * rstd * m2);
+    t.w = rstd * (d.w * (1.0f + g.w) - m1 - (v.w - mean) * rstd * m2);
+    const size_t o = spix * p.dx_Cs + 4 * i;
+    if (p.dx_acc) {
+      const float4 old = ld4(p.dx, 2, o);
+      t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+    }
+    st4(p.dx, 2, o, t);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- instance norm
+// stats[b][c] = {sum, sumsq} over the H*W pixels; blockDim (32 channels-quads?, 8): thread x owns 4 channels.
+// grid (pixel chunks, channel groups of 128, B); partial sums land with atomics (stats zeroed by the launcher).
+__global__ void __launch_bounds__(256)
+in_stats_nhwc_kernel(const void* __restrict__ x, int kind, int Cs, int C, int HW, int pix_per_block,
+                     float* __restrict__ stats) {
+  __shared__ float red[8][32][8];
+  const int b = blockIdx.z;
+  const int c = blockIdx.y * 128 + threadIdx.x * 4;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block;
+  if (p1 > HW) p1 = HW;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
+      const float4 v = ld4(x, kind, (static_cast<size_t>(b) * HW + pix) * Cs + c);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.y][threadIdx.x][j] = s[j];
+    red[threadIdx.y][threadIdx.x][4 + j] = q[j];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f, bq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a += red[k][threadIdx.x][j];
+        bq += red[k][threadIdx.x][4 + j];
+      }
+      if (c + j < C) {
+        atomicAdd(stats + (static_cast<size_t>(b) * C + c + j) * 2, a);
+        atomicAdd(stats + (static_cast<size_t>(b) * C + c + j) * 2 + 1, bq);
+      }
+    }
+  }
+}
+
+struct InstFwd {
+  const void* x; int x_kind, x_Cs;
+  const float* stats;                    // [B, C, 2] sum / sumsq
+  const void* res; int res_kind, res_Cs; // optional residual added after the normalisation
+  const float* slope_ptr; float slope;   // PReLU parameter (device scalar) or a constant slope (1 = none)
+  void* y; int y_kind, y_Cs, y_lo_off, y_pad;   // op (fp16 [+lo], halo) or any kind without halo
+  void* y2; int y2_Cs;                   // optional second output: fp32 NHWC, no halo (residual source of the next block)
+  int B, C, H, W;
+  float eps;
+};
+
+// one thread per 4 channels of one (padded) output pixel
+__global__ void __launch_bounds__(256) inst_act_nhwc_fwd_kernel(const InstFwd p) {
+  const int Hp = p.H + 2 * p.y_pad, Wp = p.W + 2 * p.y_pad;
+  const int n4 = p.C >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(p.B) * Hp * Wp * n4) return;
+  const int c = static_cast<int>(idx % n4) * 4;
+  const long long op = idx / n4;
+  const int b = static_cast<int>(op / (Hp * Wp));
+  const int r = static_cast<int>(op - static_cast<long long>(b) * Hp * Wp);
+  const int ho = r / Wp, wo = r - ho * Wp;
+  const int hs = reflect1(ho - p.y_pad, p.H), ws = reflect1(wo - p.y_pad, p.W);
+  const size_t spix = (static_cast<size_t>(b) * p.H + hs) * p.W + ws;
+  const float inv = 1.0f / (p.H * p.W);
+  const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
+  const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
+  float in[4] = {v.x, v.y, v.z, v.w}, out[4];
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.res) {
+    const float4 t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
+    rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
+    const float mean = st[0] * inv;
+    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
+    const float z = (in[j] - mean) * rsqrtf(var + p.eps) + rs[j];
+    out[j] = lrelu(z, slope);
+  }
+  const float4 o = make_float4(out[0], out[1], out[2], out[3]);
+  const size_t yo = static_cast<size_t>(op) * p.y_Cs + c;
+  st4(p.y, p.y_kind, yo, o);
+  if (p.y_lo_off) st4(p.y, 1, yo + p.y_lo_off, lo4(o));
+  if (p.y2 && ho - p.y_pad == hs && wo - p.y_pad == ws) st4(p.y2, 3, spix * p.y2_Cs + c, o);
+}
+
+struct InstBwd {
+  const void* dy; int dy_Cs, dy_pad;     // bf16 [B, H+2p, W+2p, dy_Cs]
+  const void* dy2; int dy2_Cs;           // optional second upstream gradient (of y2), bf16 [B,H,W,dy2_Cs]
+  const void* x; int x_kind, x_Cs;
+  const float* stats;
+  const void* res; int res_kind, res_Cs;
+  const float* slope_ptr; float slope;
+  float* bstats;                         // [B, C, 2]: sum dz, sum dz*z (pass 1 output, pass 2 input)
+  float* dslope;                         // optional PReLU gradient accumulator (pass 1)
+  void* dx; int dx_Cs, dx_acc;           // bf16
+  void* dres; int dres_Cs, dres_acc;     // optional bf16
+  int B, C, H, W;
+  float eps;
+};
+
+// dz for 4 channels of one source pixel (shared by both passes)
+__device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, int b, int h, int w, int c, float slope, float* z,
+                                            float* dz, float* u_neg_dy) {
+  const int Wp = p.W + 2 * p.dy_pad, Hp = p.H + 2 * p.dy_pad;
+  const size_t spix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+  const Fold f = make_fold(h, w, p.H, p.W, p.dy_pad);
+  float4 d = folded4(p.dy, 2, f, static_cast<size_t>(b) * Hp * Wp, Wp, p.dy_Cs, c);
+  if (p.dy2) {
+    const float4 t = ld4(p.dy2, 2, spix * p.dy2_Cs + c);
+    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+  }
+  const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.res) {
+    const float4 t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
+    rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
+  }
+  const float in[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  const float inv = 1.0f / (p.H * p.W);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
+    const float mean = st[0] * inv;
+    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
+    z[j] = (in[j] - mean) * rsqrtf(var + p.eps);
+    const float u = z[j] + rs[j];
+    dz[j] = u > 0.f ? dd[j] : dd[j] * slope;
+    u_neg_dy[j] = u > 0.f ? 0.f : dd[j] * u;
+  }
+}
+
+// pass 1: bstats += {sum dz, sum dz*z}, dslope += sum dy*u*[u<=0]; grid (pixel chunks, channel groups of 128, B)
+__global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const InstBwd p, int pix_per_block) {
+  __shared__ float red[8][32][8];
+  __shared__ float red_s[8][32];
+  const int b = blockIdx.z;
+  const int c = blockIdx.y * 128 + threadIdx.x * 4;
+  const int HW = p.H * p.W;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block;
+  if (p1 > HW) p1 = HW;
+  const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
+  if (c < p.C) {
+    for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
+      const int h = pix / p.W, w = pix - h * p.W;
+      float z[4], dz[4], un[4];
+      inst_bwd_dz(p, b, h, w, c, slope, z, dz, un);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += dz[j];
+        q[j] = fmaf(dz[j], z[j], q[j]);
+        ds += un[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.y][threadIdx.x][j] = s[j];
+    red[threadIdx.y][threadIdx.x][4 + j] = q[j];
+  }
+  red_s[threadIdx.y][threadIdx.x] = ds;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    if (c < p.C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = 0.f, bq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a += red[k][threadIdx.x][j];
+          bq += red[k][threadIdx.x][4 + j];
+        }
+        if (c + j < p.C) {
+          atomicAdd(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2, a);
+          atomicAdd(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2 + 1, bq);
+        }
+      }
+    }
+    if (p.dslope) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red_s[k][threadIdx.x];
+      t = warp_sum(t);
+      if (threadIdx.x == 0) atomicAdd(p.dslope, t);
+    }
+  }
+}
+
+// pass 2: dx = rstd * (dz - mean(dz) - z * mean(dz*z)); dres = dz
+__global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const InstBwd p) {
+  const int n4 = p.C >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(p.B) * p.H * p.W * n4) return;
+  const int c = static_cast<int>(idx % n4) * 4;
+  const long long pixl = idx / n4;
+  const int b = static_cast<int>(pixl / (p.H * p.W));
+  const int r = static_cast<int>(pixl - static_cast<long long>(b) * p.H * p.W);
+  const int h = r / p.W, w = r - h * p.W;
+  const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
+  float z[4], dz[4], un[4], o[4];
+  inst_bwd_dz(p, b, h, w, c, slope, z, dz, un);
+  const float inv = 1.0f / (p.H * p.W);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
+    const float* bs = p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2;
+    const float mean = st[0] * inv;
+    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
+    o[j] = rsqrtf(var + p.eps) * (dz[j] - bs[0] * inv - z[j] * bs[1] * inv);
+  }
+  const size_t spix = static_cast<size_t>(pixl);
+  float4 t = make_float4(o[0], o[1], o[2], o[3]);
+  if (p.dx_acc) {
+    const float4 old = ld4(p.dx, 2, spix * p.dx_Cs + c);
+    t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+  }
+  st4(p.dx, 2, spix * p.dx_Cs + c, t);
+  if (p.dres) {
+    float4 t2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    if (p.dres_acc) {
+      const float4 old = ld4(p.dres, 2, spix * p.dres_Cs + c);
+      t2.x += old.x; t2.y += old.y; t2.z += old.z; t2.w += old.w;
+    }
+    st4(p.dres, 2, spix * p.dres_Cs + c, t2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- pack / unpack
+// fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2p, W+2p, Cs]: dst pixel (h, w) = src pixel (h*f, w*f)
+// (nearest down-sampling by the integer factor f, F.interpolate(mode='nearest')), reflection halo, channels
+// [C, Cs) zero, optional lo term.  blockDim (32, 8): smem-tiled transpose, 32 pixels x 32 channels per block.
+__global__ void __launch_bounds__(256)
+nhwc_pack_kernel(const float* __restrict__ src, void* __restrict__ dst, int kind, int C, int Cs, int cspan, int lo_off,
+                 int Hs, int Ws, int H, int W, int f, int pad) {
+  __shared__ float tile[32][33];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int op0 = blockIdx.x * 32;
+  // load: thread x = pixel, thread y (+8k) = channel
+  {
+    const int op = op0 + threadIdx.x;
+    const bool live = op < Hp * Wp;
+    const int opc = live ? op : 0;
+    const int ho = opc / Wp, wo = opc - ho * Wp;
+    const int hs = reflect1(ho - pad, H) * f, ws = reflect1(wo - pad, W) * f;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int c = c0 + threadIdx.y + k;
+      tile[threadIdx.y + k][threadIdx.x] =
+          (live && c < C) ? src[((static_cast<size_t>(b) * C + c) * Hs + hs) * Ws + ws] : 0.f;
+    }
+  }
+  __syncthreads();
+  // store: thread x = channel, thread y (+8k) = pixel
+  const int c = c0 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int op = op0 + threadIdx.y + k;
+    if (op < Hp * Wp && c < cspan) {
+      const float v = tile[threadIdx.x][threadIdx.y + k];
+      const size_t o = (static_cast<size_t>(b) * Hp * Wp + op) * Cs + c;
+      if (kind == 3) static_cast<float*>(dst)[o] = v;
+      else if (kind == 2) static_cast<uint16_t*>(dst)[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+      else {
+        static_cast<uint16_t*>(dst)[o] = __half_as_ushort(__float2half_rn(v));
+        if (lo_off) static_cast<uint16_t*>(dst)[o + lo_off] = __half_as_ushort(__float2half_rn(lo16(v)));
+      }
+    }
+  }
+}
+
+// NHWC kind `kind` [B, H+2p, W+2p, Cs] (channels [c_lo, c_lo + C)) -> fp32 NCHW [B, Cd, Hd, Wd] channels
+// [cd_lo, cd_lo + C) at pixels (h*f, w*f); the reflection halo is folded back; acc: add instead of overwrite.
+__global__ void __launch_bounds__(256)
+nhwc_unpack_kernel(const void* __restrict__ src, int kind, int Cs, int c_lo, int C, int H, int W, int pad,
+                   float* __restrict__ dst, int Cd, int cd_lo, int Hd, int Wd, int f, int acc) {
+  __shared__ float tile[32][33];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int p0 = blockIdx.x * 32;
+  {
+    const int c = c0 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int pix = p0 + threadIdx.y + k;
+      float v = 0.f;
+      if (pix < H * W && c < C) {
+        const int h = pix / W, w = pix - h * W;
+        const Fold fo = make_fold(h, w, H, W, pad);
+        for (int a = 0; a < fo.nh; ++a)
+          for (int e = 0; e < fo.nw; ++e) {
+            const size_t o = ((static_cast<size_t>(b) * Hp + fo.hc[a]) * Wp + fo.wc[e]) * Cs + c_lo + c;
+            if (kind == 3) v += static_cast<const float*>(src)[o];
+            else if (kind == 2) v += __bfloat162float(__ushort_as_bfloat16(static_cast<const uint16_t*>(src)[o]));
+            else v += __half2float(__ushort_as_half(static_cast<const uint16_t*>(src)[o]));
+          }
+      }
+      tile[threadIdx.y + k][threadIdx.x] = v;
+    }
+  }
+  __syncthreads();
+  const int pix = p0 + threadIdx.x;
+  if (pix < H * W) {
+    const int h = pix / W, w = pix - h * W;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int c = c0 + threadIdx.y + k;
+      if (c < C) {
+        float* d = dst + ((static_cast<size_t>(b) * Cd + cd_lo + c) * Hd + static_cast<size_t>(h) * f) * Wd +
+                   static_cast<size_t>(w) * f;
+        const float v = tile[threadIdx.x][threadIdx.y + k];
+        *d = acc ? *d + v : v;
+      }
+    }
+  }
+}
+
+// db[c] += sum over rows of a 16-bit / fp32 [rows, Cs] matrix (out zeroed by the launcher); grid (row chunks, C/128)
+__global__ void __launch_bounds__(256)
+colsum_nhwc_kernel(const void* __restrict__ x, int kind, int Cs, int C, long long rows, int rows_per_block,
+                   float* __restrict__ out) {
+  __shared__ float red[8][32][4];
+  const int c = blockIdx.y * 128 + threadIdx.x * 4;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 v = ld4(x, kind, static_cast<size_t>(r) * Cs + c);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][threadIdx.x][j];
+      if (c + j < C) atomicAdd(out + c + j, a);
+    }
+  }
+}
+
+// Weight matrix of a tap-group list: dst[row][g*Kc + c] for row < rows (rows_alloc >= rows: the rest zero),
+// g < ngroups, c < Kc.  transposed == 0 (forward): row = output channel, c = input channel, value = W[row][c][r][s];
+// transposed == 1 (backward-data): row = input channel, c = output channel, value = W[c][row][r][s].
+// term 0: the 16-bit rounding of the value; term 1: lo = fp16(value - fp16(value)).
+struct PackW {
+  const float* w; int Cout, Cin, KS;
+  void* dst; int rows, rows_alloc, Kc, ngroups, transposed, bf16;
+  int8_t r[COCOS_TAPCONV_MAX_GROUPS], s[COCOS_TAPCONV_MAX_GROUPS], term[COCOS_TAPCONV_MAX_GROUPS];
+};
+__global__ void __launch_bounds__(256) pack_w_kernel(const PackW p) {
+  const long long Kt = static_cast<long long>(p.ngroups) * p.Kc;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= p.rows_alloc * Kt) return;
+  const int row = static_cast<int>(idx / Kt);
+  const int k = static_cast<int>(idx - row * Kt);
+  const int g = k / p.Kc, c = k - g * p.Kc;
+  float v = 0.f;
+  const int nc = p.transposed ? p.Cout : p.Cin;
+  if (row < p.rows && c < nc) {
+    const int co = p.transposed ? c : row, ci = p.transposed ? row : c;
+    v = p.w[((static_cast<size_t>(co) * p.Cin + ci) * p.KS + p.r[g]) * p.KS + p.s[g]];
+  }
+  uint16_t bits;
+  if (p.bf16) bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  else bits = __half_as_ushort(__float2half_rn(p.term[g] ? lo16(v) : v));
+  static_cast<uint16_t*>(p.dst)[idx] = bits;
+}
+
+inline int blocks_for(long long n, int per) { return static_cast<int>((n + per - 1) / per); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- launchers
+int spade_mod_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
+                              int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
+                              float slope, float eps, cudaStream_t stream) {
+  if (B <= 0 || C < 4 || (C % 4) || H <= pad || W <= pad || pad < 0 || pad > 1 || (x_Cs % 4) || (gb_Cs % 4) ||
+      (y_Cs % 4) || (y_lo_off % 4) || (x_kind != 1 && x_kind != 3) || (gb_kind != 1 && gb_kind != 3)) {
+    set_error("spade_mod_nhwc_fwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+    return -1;
+  }
+  SpadeFwd p{x, x_kind, x_Cs, gb, gb_kind, gb_Cs, y, y_Cs, y_lo_off, mean, rstd, B, C, H, W, pad, slope, eps};
+  const long long pix = static_cast<long long>(B) * (H + 2 * pad) * (W + 2 * pad);
+  spade_mod_nhwc_fwd_kernel<<<blocks_for(pix, 8), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int spade_mod_nhwc_bwd_launch(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
+                              int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
+                              int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
+                              cudaStream_t stream) {
+  if (B <= 0 || C < 4 || (C % 4) || H <= pad || W <= pad || pad < 0 || pad > 1 || (dy_Cs % 4) || (x_Cs % 4) ||
+      (gb_Cs % 4) || (dx_Cs % 4) || (dgb_Cs % 4) || (x_kind != 1 && x_kind != 3) || (gb_kind != 1 && gb_kind != 3)) {
+    set_error("spade_mod_nhwc_bwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
+    return -1;
+  }
+  SpadeBwd p{dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, mean, rstd, dx, dx_Cs, dx_acc, dgb, dgb_Cs,
+             B, C, H, W, pad, slope};
+  spade_mod_nhwc_bwd_kernel<<<blocks_for(static_cast<long long>(B) * H * W, 8), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int stats_grid(int HW, int C, int B, dim3* grid, int* ppb) {
+  const int cg = (C + 127) / 128;
+  // ~4 waves of blocks, at least 64 pixels per block
+  int chunks = (4 * 148 + cg * B - 1) / (cg * B);
+  const int max_chunks = (HW + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  *ppb = (HW + chunks - 1) / chunks;
+  *grid = dim3((HW + *ppb - 1) / *ppb, cg, B);
+  return 0;
+}
+
+int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || (C % 4) || (Cs % 4) || HW <= 0 || kind < 1 || kind > 3) {
+    set_error("in_stats_nhwc: bad arguments (B=%d C=%d HW=%d)", B, C, HW);
+    return -1;
+  }
+  COCOS_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * C, stream));
+  dim3 grid;
+  int ppb;
+  stats_grid(HW, C, B, &grid, &ppb);
+  in_stats_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, kind, Cs, C, HW, ppb, stats);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int inst_act_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
+                             int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
+                             int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
+                             cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || (C % 4) || (x_Cs % 4) || (y_Cs % 4) || (y_lo_off % 4) || H <= y_pad || W <= y_pad ||
+      y_pad < 0 || y_pad > 1 || x_kind < 1 || x_kind > 3 || y_kind < 1 || y_kind > 3 || (y_lo_off && y_kind != 1) ||
+      (res && (res_kind < 1 || res_kind > 3 || (res_Cs % 4))) || (y2 && (y2_Cs % 4))) {
+    set_error("inst_act_nhwc_fwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, y_pad);
+    return -1;
+  }
+  InstFwd p{x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, y, y_kind, y_Cs, y_lo_off, y_pad,
+            y2, y2_Cs, B, C, H, W, eps};
+  const long long n = static_cast<long long>(B) * (H + 2 * y_pad) * (W + 2 * y_pad) * (C / 4);
+  inst_act_nhwc_fwd_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
+                             int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
+                             const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
+                             int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
+                             cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || (C % 4) || (dy_Cs % 4) || (x_Cs % 4) || (dx_Cs % 4) || H <= dy_pad || W <= dy_pad ||
+      dy_pad < 0 || dy_pad > 1 || x_kind < 1 || x_kind > 3 || (res && (res_kind < 1 || res_kind > 3 || (res_Cs % 4))) ||
+      (dy2 && (dy2_Cs % 4)) || (dres && (dres_Cs % 4)) || !bstats) {
+    set_error("inst_act_nhwc_bwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, dy_pad);
+    return -1;
+  }
+  InstBwd p{dy, dy_Cs, dy_pad, dy2, dy2_Cs, x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, bstats,
+            dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C, H, W, eps};
+  COCOS_CUDA_CHECK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * B * C, stream));
+  dim3 grid;
+  int ppb;
+  stats_grid(H * W, C, B, &grid, &ppb);
+  inst_act_nhwc_bwd_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(p, ppb);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  const long long n = static_cast<long long>(B) * H * W * (C / 4);
+  inst_act_nhwc_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
+                     int W, int f, int pad, cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || Cs < C || H <= pad || W <= pad || f < 1 || (H - 1) * f >= Hs || (W - 1) * f >= Ws || pad < 0 ||
+      pad > 1 || kind < 1 || kind > 3 || (lo_off && (kind != 1 || lo_off < C || 2 * lo_off != Cs))) {
+    set_error("nhwc_pack: bad arguments (B=%d C=%d Cs=%d Hs=%d Ws=%d H=%d W=%d f=%d pad=%d)", B, C, Cs, Hs, Ws, H, W, f,
+              pad);
+    return -1;
+  }
+  const int npix = (H + 2 * pad) * (W + 2 * pad);
+  const int cspan = lo_off ? lo_off : Cs;  // channels [cspan, Cs) of a split tensor are written as lo terms
+  dim3 grid((npix + 31) / 32, (cspan + 31) / 32, B);
+  nhwc_pack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, dst, kind, C, Cs, cspan, lo_off, Hs, Ws, H, W, f, pad);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,
+                       int Cd, int cd_lo, int Hd, int Wd, int f, int acc, cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || c_lo < 0 || c_lo + C > Cs || cd_lo < 0 || cd_lo + C > Cd || H <= pad || W <= pad || f < 1 ||
+      (H - 1) * f >= Hd || (W - 1) * f >= Wd || pad < 0 || pad > 1 || kind < 1 || kind > 3) {
+    set_error("nhwc_unpack: bad arguments (B=%d C=%d Cs=%d H=%d W=%d f=%d pad=%d)", B, C, Cs, H, W, f, pad);
+    return -1;
+  }
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  nhwc_unpack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, kind, Cs, c_lo, C, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f,
+                                                        acc);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int colsum_nhwc_launch(const void* x, int kind, int Cs, int C, long long rows, float* out, cudaStream_t stream) {
+  if (C <= 0 || (C % 4) || (Cs % 4) || rows <= 0 || kind < 1 || kind > 3) {
+    set_error("colsum_nhwc: bad arguments (C=%d Cs=%d rows=%lld)", C, Cs, rows);
+    return -1;
+  }
+  COCOS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * C, stream));
+  const int cg = (C + 127) / 128;
+  long long chunks = (4 * 148 + cg - 1) / cg;
+  const long long max_chunks = (rows + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  const int rpb = static_cast<int>((rows + chunks - 1) / chunks);
+  dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb), cg);
+  colsum_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, kind, Cs, C, rows, rpb, out);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pack_w_launch(const float* w, int Cout, int Cin, int KS, void* dst, int rows, int rows_alloc, int Kc, int ngroups,
+                  const signed char* r, const signed char* s, const signed char* term, int transposed, int bf16,
+                  cudaStream_t stream) {
+  if (!w || !dst || !r || !s || !term || Cout <= 0 || Cin <= 0 || KS <= 0 || rows <= 0 || rows_alloc < rows || Kc <= 0 ||
+      (Kc % 64) || ngroups <= 0 || ngroups > COCOS_TAPCONV_MAX_GROUPS) {
+    set_error("pack_w: bad arguments (Cout=%d Cin=%d KS=%d rows=%d Kc=%d groups=%d)", Cout, Cin, KS, rows, Kc, ngroups);
+    return -1;
+  }
+  PackW p;
+  p.w = w; p.Cout = Cout; p.Cin = Cin; p.KS = KS; p.dst = dst; p.rows = rows; p.rows_alloc = rows_alloc; p.Kc = Kc;
+  p.ngroups = ngroups; p.transposed = transposed; p.bf16 = bf16;
+  for (int g = 0; g < ngroups; ++g) {
+    if (r[g] < 0 || r[g] >= KS || s[g] < 0 || s[g] >= KS) {
+      set_error("pack_w: tap (%d,%d) of group %d outside the %dx%d filter", r[g], s[g], g, KS, KS);
+      return -1;
+    }
+    p.r[g] = r[g]; p.s[g] = s[g]; p.term[g] = term[g];
+  }
+  const long long n = static_cast<long long>(rows_alloc) * ngroups * Kc;
+  pack_w_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cocos

@@ -90,6 +90,31 @@ int make_tmap_f16_4d(CUtensorMap* map, const void* base, const uint64_t dims[4],
   return 0;
 }
 
+int make_tmap_16_5d(CUtensorMap* map, const void* base, const uint64_t dims[5], const uint64_t pitches[4],
+                    const uint32_t box[5]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -3;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitches[0] & 15) || (pitches[1] & 15) || (pitches[2] & 15) ||
+      (pitches[3] & 15)) {
+    set_error("tensor map (5d): base/pitches must be 16-byte aligned");
+    return -1;
+  }
+  cuuint64_t d[5] = {dims[0], dims[1], dims[2], dims[3], dims[4]};
+  cuuint64_t st[4] = {pitches[0], pitches[1], pitches[2], pitches[3]};
+  cuuint32_t bx[5] = {box[0], box[1], box[2], box[3], box[4]};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(5d) failed: CUresult %d (dims %llu,%llu,%llu,%llu,%llu box %u,%u,%u,%u,%u)", (int)r,
+              (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)d[3],
+              (unsigned long long)d[4], bx[0], bx[1], bx[2], bx[3], bx[4]);
+    return -3;
+  }
+  return 0;
+}
+
 int make_tmap_f32_3d_plain(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                            uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2) {
   EncodeTiledFn enc = get_encode();

@@ -20,6 +20,10 @@ int make_tmap_f16_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d
 int make_tmap_f16_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t pitches[3],
                      const uint32_t box[4]);
 
+// 16-bit tensor of rank 5 (d0 contiguous), pitches in BYTES, 128B swizzle, OOB -> zero.
+int make_tmap_16_5d(CUtensorMap* map, const void* base, const uint64_t dims[5], const uint64_t pitches[4],
+                    const uint32_t box[5]);
+
 // fp32 tensor [d2][d1][d0], no swizzle (plain row-major box in shared memory), OOB -> zero fill.
 int make_tmap_f32_3d_plain(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1,
                            uint64_t pitch2, uint32_t b0, uint32_t b1, uint32_t b2);

@@ -1,0 +1,407 @@
+"""16-bit NHWC pipeline: tensor container + host-side planning of the tap convolutions + thin wrappers over the
+C-ABI (include/cocos_b200.h: cocos_tapconv, cocos_tapwgrad, cocos_pack_w, cocos_spade_mod_nhwc_*,
+cocos_inst_act_nhwc_*, cocos_nhwc_pack / unpack, cocos_colsum_nhwc).
+
+Everything here is layout / planning logic; the arithmetic runs in the sm_100a kernels.  `BACKEND` is the object
+that enqueues kernels: the native one (ctypes -> libcocos_b200.so) is the only one the product ever uses and it
+raises when the library is missing.  The CPU tests install a torch emulation of the same entry points
+(oracle/nhwc_emul.py) to check the planning logic against F.conv2d / autograd without a GPU.
+
+Reference call sites served: every nn.Conv2d of models/networks/{generator,architecture,normalization,correspondence,
+discriminator}.py plus the norm / activation / padding modules between them.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F16, BF16, F32 = 1, 2, 3
+NCHW32 = 0
+MAXG = 48
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class NT:
+    """NHWC activation: t [B, H + 2*pad, W + 2*pad, Cs]; C logical channels (the rest of Cs is zero / lo terms);
+    lo = channel offset of the fp16 residual term of a 2-term split operand (0: none)."""
+    __slots__ = ("t", "kind", "C", "pad", "lo")
+
+    def __init__(self, t, kind, C, pad=0, lo=0):
+        self.t, self.kind, self.C, self.pad, self.lo = t, kind, C, pad, lo
+
+    B = property(lambda s: s.t.shape[0])
+    H = property(lambda s: s.t.shape[1] - 2 * s.pad)
+    W = property(lambda s: s.t.shape[2] - 2 * s.pad)
+    Cs = property(lambda s: s.t.shape[3])
+
+    def __repr__(self):
+        return "NT(kind=%d, B=%d, H=%d, W=%d, C=%d, Cs=%d, pad=%d, lo=%d)" % (self.kind, self.B, self.H, self.W, self.C,
+                                                                               self.Cs, self.pad, self.lo)
+
+
+# ------------------------------------------------------------------------------------------------ tap-group plans
+class Group:
+    __slots__ = ("dh", "dw", "coff", "r", "s", "term")
+
+    def __init__(self, dh, dw, coff, r, s, term):
+        self.dh, self.dw, self.coff, self.r, self.s, self.term = dh, dw, coff, r, s, term
+
+
+def plan_fwd(ks, padding, lo_off=0):
+    """Forward conv (any stride): one group per filter tap, three with 2-term split operands
+    (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo)."""
+    groups = []
+    for r in range(ks):
+        for s in range(ks):
+            groups.append(Group(r - padding, s - padding, 0, r, s, 0))
+            if lo_off:
+                groups.append(Group(r - padding, s - padding, lo_off, r, s, 0))
+                groups.append(Group(r - padding, s - padding, 0, r, s, 1))
+    return groups
+
+
+def plan_dgrad(ks, padding, stride):
+    """Backward-data as tap convolutions over dY: list of (pi, pj, groups); stride 1: one class, stride 2: the four
+    input-pixel parity classes.  dX[s*a + pi] = sum_r dY[a + (pi + padding - r)/s] W[r] over the r of matching parity."""
+    classes = []
+    for pi in range(stride):
+        for pj in range(stride):
+            groups = []
+            for r in range(ks):
+                if (pi + padding - r) % stride:
+                    continue
+                for s in range(ks):
+                    if (pj + padding - s) % stride:
+                        continue
+                    groups.append(Group((pi + padding - r) // stride, (pj + padding - s) // stride, 0, r, s, 0))
+            classes.append((pi, pj, groups))
+    return classes
+
+
+def conv_out_size(n_in, ks, padding, stride):
+    return (n_in + 2 * padding - ks) // stride + 1
+
+
+# ------------------------------------------------------------------------------------------------ native backend
+class _TapconvDesc(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("res", ctypes.c_void_p),
+                ("y", ctypes.c_void_p)] + \
+               [(n, ctypes.c_int) for n in ("B", "Hin", "Win", "Ca", "a_stride", "bf16", "H", "W", "Cout", "w_rows",
+                                            "ngroups", "kchunks")] + \
+               [("dh", ctypes.c_byte * MAXG), ("dw", ctypes.c_byte * MAXG), ("coff", ctypes.c_short * MAXG),
+                ("res_kind", ctypes.c_int), ("res_Cs", ctypes.c_int), ("act", ctypes.c_int),
+                ("slope", ctypes.c_float)] + \
+               [(n, ctypes.c_int) for n in ("y_kind", "y_H", "y_W", "y_Cs", "y_coff", "y_lo_off", "y_pad", "y_reflect",
+                                            "y_sh", "y_sw", "y_oh", "y_ow")]
+
+
+class _TapwgradDesc(ctypes.Structure):
+    _fields_ = [("dy", ctypes.c_void_p), ("x", ctypes.c_void_p), ("ws", ctypes.c_void_p)] + \
+               [(n, ctypes.c_int) for n in ("B", "H", "W", "dy_Cs", "Cout", "Hin", "Win", "Ca", "a_stride", "x_f16",
+                                            "Cin", "Cin_s", "ngroups")] + \
+               [("dh", ctypes.c_byte * MAXG), ("dw", ctypes.c_byte * MAXG), ("coff", ctypes.c_short * MAXG)]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+_DTYPES = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
+
+
+class NativeBackend:
+    """ctypes -> libcocos_b200.so.  No fallback: constructing it without the library raises."""
+    exact = False
+
+    def __init__(self):
+        self.lib = _lib.lib()
+
+    @staticmethod
+    def dtype(kind):
+        return _DTYPES[kind]
+
+    def empty(self, shape, kind, device, zero=False):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=_DTYPES[kind], device=device)
+
+    def tapconv(self, x, w, bias, res, y, d):
+        """d: dict of the scalar descriptor fields + 'groups'."""
+        desc = _TapconvDesc()
+        desc.x, desc.w, desc.bias, desc.res, desc.y = _p(x), _p(w), _p(bias), _p(res), _p(y)
+        for k in ("B", "Hin", "Win", "Ca", "a_stride", "bf16", "H", "W", "Cout", "w_rows", "kchunks", "res_kind", "res_Cs",
+                  "act", "y_kind", "y_H", "y_W", "y_Cs", "y_coff", "y_lo_off", "y_pad", "y_reflect", "y_sh", "y_sw",
+                  "y_oh", "y_ow"):
+            setattr(desc, k, int(d[k]))
+        desc.slope = float(d["slope"])
+        groups = d["groups"]
+        desc.ngroups = len(groups)
+        for i, g in enumerate(groups):
+            desc.dh[i], desc.dw[i], desc.coff[i] = g.dh, g.dw, g.coff
+        _lib.check(self.lib.cocos_tapconv(ctypes.byref(desc), _stream()), "cocos_tapconv")
+
+    def tapwgrad(self, dy, x, ws, d):
+        desc = _TapwgradDesc()
+        desc.dy, desc.x, desc.ws = _p(dy), _p(x), _p(ws)
+        for k in ("B", "H", "W", "dy_Cs", "Cout", "Hin", "Win", "Ca", "a_stride", "x_f16", "Cin", "Cin_s"):
+            setattr(desc, k, int(d[k]))
+        groups = d["groups"]
+        desc.ngroups = len(groups)
+        for i, g in enumerate(groups):
+            desc.dh[i], desc.dw[i], desc.coff[i] = g.dh, g.dw, g.coff
+        _lib.check(self.lib.cocos_tapwgrad(ctypes.byref(desc), _stream()), "cocos_tapwgrad")
+
+    def pack_w(self, w, dst, rows, rows_alloc, kc, groups, transposed, bf16):
+        n = len(groups)
+        arr = lambda vals: (ctypes.c_byte * n)(*vals)  # noqa: E731
+        cout, cin, ks, _ = w.shape
+        _lib.check(self.lib.cocos_pack_w(w.data_ptr(), cout, cin, ks, dst.data_ptr(), rows, rows_alloc, kc, n,
+                                         arr([g.r for g in groups]), arr([g.s for g in groups]),
+                                         arr([g.term for g in groups]), int(transposed), int(bf16), _stream()),
+                   "cocos_pack_w")
+
+    def spade_fwd(self, x, gb, y, mean, rstd, C, pad, slope, eps):
+        _lib.check(self.lib.cocos_spade_mod_nhwc_fwd(x.t.data_ptr(), x.kind, x.Cs, gb.t.data_ptr(), gb.kind, gb.Cs,
+                                                     y.t.data_ptr(), y.Cs, y.lo, mean.data_ptr(), rstd.data_ptr(),
+                                                     x.B, C, x.H, x.W, pad, float(slope), float(eps), _stream()),
+                   "cocos_spade_mod_nhwc_fwd")
+
+    def spade_bwd(self, dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope):
+        _lib.check(self.lib.cocos_spade_mod_nhwc_bwd(dy.t.data_ptr(), dy.Cs, x.t.data_ptr(), x.kind, x.Cs,
+                                                     gb.t.data_ptr(), gb.kind, gb.Cs, mean.data_ptr(), rstd.data_ptr(),
+                                                     dx.t.data_ptr(), dx.Cs, int(dx_acc), dgb.t.data_ptr(), dgb.Cs,
+                                                     x.B, C, x.H, x.W, pad, float(slope), _stream()),
+                   "cocos_spade_mod_nhwc_bwd")
+
+    def in_stats(self, x, stats, C):
+        _lib.check(self.lib.cocos_in_stats_nhwc(x.t.data_ptr(), x.kind, x.Cs, x.B, C, x.H * x.W, stats.data_ptr(),
+                                                _stream()), "cocos_in_stats_nhwc", kernels=2)
+
+    def inst_fwd(self, x, stats, res, slope_ptr, slope, y, y2, eps, C):
+        _lib.check(self.lib.cocos_inst_act_nhwc_fwd(
+            x.t.data_ptr(), x.kind, x.Cs, stats.data_ptr(), _p(res.t if res else None), res.kind if res else 0,
+            res.Cs if res else 0, _p(slope_ptr), float(slope), y.t.data_ptr(), y.kind, y.Cs, y.lo, y.pad,
+            _p(y2.t if y2 else None), y2.Cs if y2 else 0, x.B, C, x.H, x.W, float(eps), _stream()),
+            "cocos_inst_act_nhwc_fwd")
+
+    def inst_bwd(self, dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C):
+        _lib.check(self.lib.cocos_inst_act_nhwc_bwd(
+            dy.t.data_ptr(), dy.Cs, dy.pad, _p(dy2.t if dy2 else None), dy2.Cs if dy2 else 0, x.t.data_ptr(), x.kind,
+            x.Cs, stats.data_ptr(), _p(res.t if res else None), res.kind if res else 0, res.Cs if res else 0,
+            _p(slope_ptr), float(slope), bstats.data_ptr(), _p(dslope), dx.t.data_ptr(), dx.Cs, int(dx_acc),
+            _p(dres.t if dres else None), dres.Cs if dres else 0, int(dres_acc), x.B, C, x.H, x.W, float(eps),
+            _stream()), "cocos_inst_act_nhwc_bwd", kernels=3)
+
+    def pack(self, src, dst, C, f):
+        b, _, hs, ws = src.shape
+        _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, hs, ws,
+                                            dst.H, dst.W, f, dst.pad, _stream()), "cocos_nhwc_pack")
+
+    def unpack(self, src, c_lo, C, dst, cd_lo, f, acc):
+        _lib.check(self.lib.cocos_nhwc_unpack(src.t.data_ptr(), src.kind, src.Cs, c_lo, C, src.B, src.H, src.W, src.pad,
+                                              dst.data_ptr(), dst.shape[1], cd_lo, dst.shape[2], dst.shape[3], f,
+                                              int(acc), _stream()), "cocos_nhwc_unpack")
+
+    def colsum(self, x2d, kind, Cs, C, rows, out):
+        _lib.check(self.lib.cocos_colsum_nhwc(x2d.data_ptr(), kind, Cs, C, rows, out.data_ptr(), _stream()),
+                   "cocos_colsum_nhwc", kernels=2)
+
+
+_BACKEND = None
+
+
+def backend():
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = NativeBackend()
+    return _BACKEND
+
+
+def set_backend(b):
+    """Tests only (oracle/nhwc_emul.py); returns the previous backend."""
+    global _BACKEND
+    old, _BACKEND = _BACKEND, b
+    return old
+
+
+# ------------------------------------------------------------------------------------------------ tensor helpers
+def new(B, H, W, C, kind, device, pad=0, split=False, Cs=None, zero=None):
+    """Allocate an NT.  Channels beyond C (padding up to a multiple of 8) must be finite: zero-filled when they exist
+    unless the producer writes them."""
+    cp = round_up(C, 8)
+    if Cs is None:
+        Cs = 2 * cp if split else cp
+    lo = cp if split else 0
+    if zero is None:
+        zero = cp != C
+    t = backend().empty((B, H + 2 * pad, W + 2 * pad, Cs), kind, device, zero=zero)
+    return NT(t, kind, C, pad, lo)
+
+
+def pack(src, kind=F16, pad=0, split=False, f=1, size=None):
+    """fp32 NCHW -> NT (nearest down-sampling by the integer factor f to `size`, reflection halo, split)."""
+    src = src.contiguous()
+    b, c, hs, ws = src.shape
+    h, w = size if size is not None else (hs // f, ws // f)
+    out = new(b, h, w, c, kind, src.device, pad=pad, split=split, zero=False)
+    backend().pack(src, out, c, f)
+    return out
+
+
+def unpack(x, c_lo=0, C=None, out=None, cd_lo=0, f=1, acc=False):
+    """NT -> fp32 NCHW (halo folded back by summation: the adjoint of the reflection padding)."""
+    C = x.C - c_lo if C is None else C
+    if out is None:
+        out = torch.empty((x.B, C, x.H * f, x.W * f), dtype=torch.float32, device=x.t.device)
+        assert f == 1 and not acc
+    backend().unpack(x, c_lo, C, out, cd_lo, f, acc)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def _pack_weight(weight, groups, rows, kc, transposed, bf16):
+    be = backend()
+    rows_alloc = round_up(rows, 128)
+    dst = be.empty((rows_alloc, len(groups) * kc), BF16 if bf16 else F16, weight.device)
+    be.pack_w(weight.detach().contiguous(), dst, rows, rows_alloc, kc, groups, transposed, bf16)
+    return dst, rows_alloc
+
+
+def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kind=F16, out_pad=0, split_out=False,
+         res=None, nchw_out=None, nchw_coff=0):
+    """nn.Conv2d forward on the tap-convolution kernel.  x: NT fp16 (its tensor, halo included, IS the conv input;
+    `padding` is the module's zero padding).  Returns an NT of kind out_kind (op tensors: out_pad = 1 adds the
+    reflection halo of the next conv, split_out the lo term), or writes fp32 NCHW into `nchw_out` (channels from
+    nchw_coff) and returns it."""
+    assert x.kind == F16, "forward operands are fp16"
+    cout, cin, ks, _ = weight.shape
+    assert cin == x.C, (cin, x.C)
+    hin, win = x.t.shape[1], x.t.shape[2]
+    h, w = conv_out_size(hin, ks, padding, stride), conv_out_size(win, ks, padding, stride)
+    groups = plan_fwd(ks, padding, x.lo)
+    kchunks = (cin + 63) // 64
+    wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False)
+    d = dict(B=x.B, Hin=hin, Win=win, Ca=x.Cs, a_stride=stride, bf16=0, H=h, W=w, Cout=cout, w_rows=rows_alloc,
+             kchunks=kchunks, groups=groups, res_kind=res.kind if res else 0, res_Cs=res.Cs if res else 0, act=act,
+             slope=slope, y_H=h, y_W=w, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=1, y_sw=1, y_oh=0, y_ow=0)
+    if res is not None:
+        assert res.pad == 0 and res.H == h and res.W == w and res.C == cout
+    if nchw_out is not None:
+        d.update(y_kind=NCHW32, y_Cs=nchw_out.shape[1], y_coff=nchw_coff)
+        assert tuple(nchw_out.shape[2:]) == (h, w) and nchw_out.is_contiguous()
+        backend().tapconv(x.t, wp, bias, res.t if res else None, nchw_out, d)
+        return nchw_out
+    out = new(x.B, h, w, cout, out_kind, x.t.device, pad=out_pad, split=split_out)
+    d.update(y_kind=out_kind, y_Cs=out.Cs, y_lo_off=out.lo, y_pad=out_pad, y_reflect=1 if out_pad else 0)
+    backend().tapconv(x.t, wp, bias, res.t if res else None, out.t, d)
+    return out
+
+
+def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=None):
+    """Backward-data: dy NT bf16 [B,H,W,Cout] -> gradient w.r.t. the conv input tensor (halo included) as an NT bf16
+    with pad = in_pad (the consumer folds the halo).  in_hw = (Hin, Win) of the input tensor incl. halo.
+    c_lo / c_n: only input channels [c_lo, c_lo + c_n) are produced."""
+    assert dy.kind == BF16 and dy.pad == 0
+    cout, cin, ks, _ = weight.shape
+    assert cout == dy.C
+    hin, win = in_hw
+    if c_n is None:
+        c_n = cin - c_lo
+    wsub = weight if (c_lo == 0 and c_n == cin) else weight[:, c_lo:c_lo + c_n]
+    kchunks = (cout + 63) // 64
+    out = new(dy.B, hin - 2 * in_pad, win - 2 * in_pad, c_n, BF16, dy.t.device, pad=in_pad)
+    for pi, pj, groups in plan_dgrad(ks, padding, stride):
+        wp, rows_alloc = _pack_weight(wsub, groups, c_n, kchunks * 64, True, True)
+        hc, wc = (hin - pi + stride - 1) // stride, (win - pj + stride - 1) // stride
+        d = dict(B=dy.B, Hin=dy.t.shape[1], Win=dy.t.shape[2], Ca=dy.Cs, a_stride=1, bf16=1, H=hc, W=wc, Cout=c_n,
+                 w_rows=rows_alloc, kchunks=kchunks, groups=groups, res_kind=0, res_Cs=0, act=ACT_NONE, slope=0.0,
+                 y_kind=BF16, y_H=hin, y_W=win, y_Cs=out.Cs, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=stride,
+                 y_sw=stride, y_oh=pi, y_ow=pj)
+        backend().tapconv(dy.t, wp, None, None, out.t, d)
+    return out
+
+
+def conv_wgrad(dy, x, ks, stride=1, padding=0):
+    """Backward-weights: dy NT bf16, x the NT the forward read (fp16, or bf16) -> dW fp32 [Cout, Cin, KS, KS]."""
+    assert dy.kind == BF16 and dy.pad == 0 and x.kind in (F16, BF16)
+    groups = plan_fwd(ks, padding, 0)
+    cin, cout = x.C, dy.C
+    cin_s = round_up(cin, 4)
+    ws = torch.empty((len(groups), cout, cin_s), dtype=torch.float32, device=dy.t.device)
+    d = dict(B=dy.B, H=dy.H, W=dy.W, dy_Cs=dy.Cs, Cout=cout, Hin=x.t.shape[1], Win=x.t.shape[2], Ca=x.Cs,
+             a_stride=stride, x_f16=1 if x.kind == F16 else 0, Cin=cin, Cin_s=cin_s, groups=groups)
+    backend().tapwgrad(dy.t, x.t, ws, d)
+    return ws[:, :, :cin].view(ks, ks, cout, cin).permute(2, 3, 0, 1).contiguous()
+
+
+def bias_grad(dy):
+    """db[c] = sum over pixels of dy (bf16 NT, no halo)."""
+    assert dy.pad == 0
+    c4 = round_up(dy.C, 4)
+    out = torch.empty((c4,), dtype=torch.float32, device=dy.t.device)
+    backend().colsum(dy.t, dy.kind, dy.Cs, c4 if c4 <= dy.Cs else dy.C, dy.B * dy.H * dy.W, out)
+    return out[:dy.C]
+
+
+# ------------------------------------------------------------------------------------------------ norm / act ops
+def spade_mod_fwd(x, gb, C, pad=0, slope=1.0, eps=1e-5, split_out=False):
+    """raw x [.., C], raw gb [.., 2C] -> op fp16 (halo pad, lo term) + (mean, rstd) for the backward."""
+    assert x.pad == 0 and gb.pad == 0 and x.kind in (F16, F32) and gb.kind in (F16, F32) and gb.C == 2 * C and x.C == C
+    y = new(x.B, x.H, x.W, C, F16, x.t.device, pad=pad, split=split_out)
+    mean = torch.empty((x.B, x.H, x.W), dtype=torch.float32, device=x.t.device)
+    rstd = torch.empty_like(mean)
+    backend().spade_fwd(x, gb, y, mean, rstd, C, pad, slope, eps)
+    return y, mean, rstd
+
+
+def spade_mod_bwd(dy, x, gb, mean, rstd, C, pad, slope, dx=None):
+    """dy bf16 (halo `pad`) -> (dx bf16 raw-shaped, dgb bf16).  dx given: accumulate into it."""
+    assert dy.kind == BF16 and dy.pad == pad
+    acc = dx is not None
+    if dx is None:
+        dx = new(x.B, x.H, x.W, C, BF16, x.t.device)
+    dgb = new(x.B, x.H, x.W, 2 * C, BF16, x.t.device)
+    backend().spade_bwd(dy, x, gb, mean, rstd, dx, acc, dgb, C, pad, slope)
+    return dx, dgb
+
+
+def in_stats(x):
+    """InstanceNorm statistics [B, C4, 2] (C4 = C rounded up to 4: the zero padding channels ride along)."""
+    c4 = round_up(x.C, 4)
+    stats = torch.empty((x.B, c4, 2), dtype=torch.float32, device=x.t.device)
+    backend().in_stats(x, stats, c4)
+    return stats
+
+
+def inst_act_fwd(x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, out_kind=F16, out_pad=0, split_out=False,
+                 want_raw=False):
+    """y = act(IN(x) [+ res]); returns (y NT, y2 NT | None): y2 = fp32 copy without halo (want_raw)."""
+    assert x.pad == 0
+    y = new(x.B, x.H, x.W, x.C, out_kind, x.t.device, pad=out_pad, split=split_out, zero=False)
+    y2 = new(x.B, x.H, x.W, x.C, F32, x.t.device, zero=False) if want_raw else None
+    backend().inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, round_up(x.C, 4))
+    return y, y2
+
+
+def inst_act_bwd(dy, x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, dy2=None, dx=None, want_dres=False,
+                 dres=None, dslope=None):
+    """-> (dx bf16, dres bf16 | None).  dx / dres given: accumulate."""
+    assert dy.kind == BF16
+    c4 = round_up(x.C, 4)
+    dx_acc = dx is not None
+    if dx is None:
+        dx = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=False)
+    dres_acc = dres is not None
+    if want_dres and dres is None:
+        dres = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=False)
+    bstats = torch.empty((x.B, c4, 2), dtype=torch.float32, device=x.t.device)
+    backend().inst_bwd(dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc,
+                       dres if want_dres else None, dres_acc, eps, c4)
+    return dx, (dres if want_dres else None)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define COCOS_ABI_VERSION 1
+#define COCOS_ABI_VERSION 2
 
 int cocos_abi_version(void);
 const char* cocos_last_error(void);
@@ -152,6 +152,118 @@ int cocos_inst_act_fwd(const float* x, float* y, float* mean, float* rstd, int p
                        void* stream);
 int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, float* dx, int planes,
                        int HW, float slope, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * 16-bit NHWC pipeline (round 2): every convolution of the generator / adaptor / residual blocks / PatchGAN / VGG19 is
+ * ONE persistent tcgen05 kernel over NHWC activations, described by a list of "tap groups"; the kernels between two
+ * convolutions (normalisation, modulation, activation, halo) read and write the same 16-bit NHWC tensors, so an
+ * activation crosses HBM once per producer / consumer instead of as fp32 NCHW + transposes + re-packs.
+ * Tensor kinds: 1 = fp16, 2 = bf16, 3 = fp32 (all NHWC [B, H, W, Cs], channel stride Cs >= C); 0 = fp32 NCHW.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define COCOS_TAPCONV_MAX_GROUPS 48
+
+/* cocos_tapconv: y[b, h, w, n] = epilogue( sum_g sum_{c < 64*kchunks}
+ *                    x[b, a_stride*h + dh[g], a_stride*w + dw[g], coff[g] + c] * w[n, (g*kchunks)*64 + c] )
+ * Replaces nn.Conv2d forward (architecture.py:31-33,73-74; normalization.py:112-120; correspondence.py:17-22,79-146;
+ * discriminator.py:92-115; generator.py:47,104-113) and the backward-data half of autograd's convolution_backward for
+ * the same layers (x = dy, transposed / flipped weights; for stride-2 layers one launch per input parity class,
+ * scattered through y_sh/y_sw/y_oh/y_ow).  Reads outside the image or beyond channel Ca are zero.
+ *   x   : 16-bit (fp16, or bf16 if `bf16`) NHWC [B, Hin, Win, Ca], Ca % 8 == 0; a_stride 2 needs even Hin, Win.
+ *   w   : same 16-bit type, [w_rows >= Cout, ngroups*kchunks*64] (cocos_pack_w), rows >= Cout zero.
+ *   epilogue: + bias[n] (fp32, may be NULL), + res[b,h,w,n] (kind 1 or 3, channel stride res_Cs, may be NULL),
+ *             act 0 none / 1 ReLU / 2 LeakyReLU(slope) / 3 tanh.
+ *   y   : kind y_kind.  NHWC kinds: [B, y_H + 2*y_pad, y_W + 2*y_pad, y_Cs], channel offset y_coff; output pixel
+ *         (h, w) lands at (h*y_sh + y_oh, w*y_sw + y_ow) (+ y_pad); y_reflect fills the 1-pixel halo by reflection
+ *         (nn.ReflectionPad2d(1) of the consumer); y_lo_off != 0 (fp16 only) also stores lo = v - fp16(v) at channel
+ *         offset + y_lo_off (2-term split operand).  y_kind 0: fp32 NCHW [B, y_Cs, y_H, y_W]. */
+typedef struct cocos_tapconv_desc {
+  const void* x;
+  const void* w;
+  const float* bias;
+  const void* res;
+  void* y;
+  int B, Hin, Win, Ca, a_stride, bf16;
+  int H, W, Cout, w_rows;
+  int ngroups, kchunks;
+  signed char dh[COCOS_TAPCONV_MAX_GROUPS];
+  signed char dw[COCOS_TAPCONV_MAX_GROUPS];
+  short coff[COCOS_TAPCONV_MAX_GROUPS];
+  int res_kind, res_Cs, act;
+  float slope;
+  int y_kind, y_H, y_W, y_Cs, y_coff, y_lo_off, y_pad, y_reflect, y_sh, y_sw, y_oh, y_ow;
+} cocos_tapconv_desc;
+int cocos_tapconv(const cocos_tapconv_desc* desc, void* stream);
+
+/* cocos_tapwgrad: ws[g, n, c] = sum_{b,h,w} dy[b,h,w,n] * x[b, a_stride*h + dh[g], a_stride*w + dw[g], coff[g] + c]
+ * (the backward-weights half of convolution_backward for the layers cocos_tapconv serves).
+ *   dy : bf16 NHWC [B, H, W, dy_Cs];  x: NHWC [B, Hin, Win, Ca] as the forward read it, fp16 (x_f16 = 1: converted
+ *        to bf16 inside the kernel) or bf16;  ws: fp32 [ngroups, Cout, Cin_s], Cin_s >= Cin, Cin_s % 4 == 0, fully
+ *        overwritten (columns >= Cin undefined). */
+typedef struct cocos_tapwgrad_desc {
+  const void* dy;
+  const void* x;
+  float* ws;
+  int B, H, W, dy_Cs, Cout;
+  int Hin, Win, Ca, a_stride, x_f16;
+  int Cin, Cin_s;
+  int ngroups;
+  signed char dh[COCOS_TAPCONV_MAX_GROUPS];
+  signed char dw[COCOS_TAPCONV_MAX_GROUPS];
+  short coff[COCOS_TAPCONV_MAX_GROUPS];
+} cocos_tapwgrad_desc;
+int cocos_tapwgrad(const cocos_tapwgrad_desc* desc, void* stream);
+
+/* Weight matrix of a tap-group list from an nn.Conv2d weight fp32 [Cout, Cin, KS, KS]:
+ * dst[row, g*Kc + c] (16-bit, fp16 or bf16) for row < rows_alloc, g < ngroups, c < Kc (Kc % 64 == 0); zero for
+ * row >= rows and beyond the channel count.  transposed 0: row = output channel, c = input channel (forward);
+ * 1: row = input channel, c = output channel (backward-data).  Group g takes filter tap (r[g], s[g]); term[g] = 1
+ * stores the fp16 residual lo = fp16(v - fp16(v)) instead of fp16(v) (2-term split). */
+int cocos_pack_w(const float* w, int Cout, int Cin, int KS, void* dst, int rows, int rows_alloc, int Kc, int ngroups,
+                 const signed char* r, const signed char* s, const signed char* term, int transposed, int bf16,
+                 void* stream);
+
+/* PONO + SPADE modulation + LeakyReLU + ReflectionPad2d over NHWC tensors (normalization.py:63-68,149;
+ * architecture.py:73-74,94-95):  y = reflect_pad_p( lrelu_slope( PONO(x) * (1 + gamma) + beta ) ).
+ * x (kind 1|3, stride x_Cs), gb (kind 1|3, stride gb_Cs; gamma = channels [0,C), beta = [C,2C)) -> y fp16
+ * [B,H+2p,W+2p,y_Cs] (+ lo term at channel offset y_lo_off if != 0); mean / rstd fp32 [B,H,W] saved for the backward:
+ * dy bf16 [B,H+2p,W+2p,dy_Cs] -> dx bf16 [B,H,W,dx_Cs] (added to the existing content if dx_acc), dgb bf16
+ * [B,H,W,dgb_Cs].  C % 4 == 0. */
+int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
+                             int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
+                             float slope, float eps, void* stream);
+int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
+                             int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
+                             int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
+                             void* stream);
+
+/* InstanceNorm2d(affine=False) statistics over NHWC: stats[b, c] = {sum, sum of squares} over the HW pixels
+ * (generator.py:104-113, discriminator.py:92-115, correspondence.py:19,23 with normalization.py:52-53). */
+int cocos_in_stats_nhwc(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, void* stream);
+
+/* y = act( instance_norm(x) [+ res] ), act = LeakyReLU(slope) or PReLU (slope_ptr: device scalar, correspondence.py:20)
+ * [, reflection halo y_pad, lo term, second fp32 copy y2 without halo].  Backward: dy bf16 (halo folded) [+ dy2] ->
+ * dx bf16, dres bf16 (optional), dslope += PReLU gradient (optional); bstats fp32 [B,C,2] scratch. */
+int cocos_inst_act_nhwc_fwd(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
+                            int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
+                            int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
+                            void* stream);
+int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
+                            int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
+                            const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
+                            int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
+                            void* stream);
+
+/* fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2*pad, W+2*pad, Cs]: nearest down-sampling by the integer
+ * factor f (F.interpolate(mode='nearest') of normalization.py:130), reflection halo, zero channels [C, Cs) and, for
+ * lo_off != 0 (fp16, Cs == 2*lo_off), the lo terms at channel offset lo_off. */
+int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
+                    int W, int f, int pad, void* stream);
+/* NHWC kind `kind` [B, H+2*pad, W+2*pad, Cs], channels [c_lo, c_lo+C), halo folded back -> fp32 NCHW
+ * dst[b, cd_lo + c, h*f, w*f] (dst is [B, Cd, Hd, Wd]); acc != 0 adds instead of overwriting. */
+int cocos_nhwc_unpack(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,
+                      int Cd, int cd_lo, int Hd, int Wd, int f, int acc, void* stream);
+/* out[c] = sum over the rows of x [rows, Cs] (kind 1|2|3), c < C: the bias gradient of a convolution. */
+int cocos_colsum_nhwc(const void* x, int kind, int Cs, int C, long long rows, float* out, void* stream);
 
 #ifdef __cplusplus
 }

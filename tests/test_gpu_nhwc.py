@@ -1,0 +1,228 @@
+"""GPU: the kernels of the 16-bit NHWC pipeline (tapconv.cu, tapwgrad.cu, ew_nhwc.cu) called through the C-ABI and
+compared with the CPU emulation of the same entry points (oracle/nhwc_emul.py, itself pinned to F.conv2d / autograd by
+tests/test_nhwc_host_logic.py) on identical 16-bit-rounded operands.  Layer shapes are the ones the ade20k / celebahq /
+deepfashion training steps run (reduced batch where the CPU emulation would take too long)."""
+import pytest
+import torch
+
+from cocosnet_b200 import nhwc
+from oracle.nhwc_emul import EmulBackend
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert torch.isfinite(a).all(), "non-finite values in the kernel output"
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def both(fn):
+    """fn(device) -> tuple of tensors; returns (native on cuda, emulation on cpu)."""
+    old = nhwc.set_backend(EmulBackend(exact=False))
+    try:
+        want = fn("cpu")
+    finally:
+        nhwc.set_backend(old)
+    got = fn("cuda")
+    torch.cuda.synchronize()
+    return got, want
+
+
+def make(case, seed=0):
+    ks, cin, cout, b, h, w = case["ks"], case["cin"], case["cout"], case["b"], case["h"], case["w"]
+    g = torch.Generator().manual_seed(seed + ks * 1000 + cin)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    return x, wt, bias, g
+
+
+CONV = {
+    # persistent multi-tile, UMMA N=256, reflection halo produced upstream (SPADE block conv_0 at 128x128)
+    "spade3x3_halo_n256": dict(ks=3, stride=1, padding=0, cin=128, cout=256, b=2, h=128, w=128, halo=1),
+    # zero padding by TMA fill, Cin = 154 (Cs 160), bias + ReLU, fp16 out with reflection halo (SPADE mlp_shared)
+    "mlp_shared_154": dict(ks=3, stride=1, padding=1, cin=154, cout=128, b=2, h=64, w=64, halo=0, act=nhwc.ACT_RELU,
+                           out_pad=1),
+    "shortcut1x1": dict(ks=1, stride=1, padding=0, cin=512, cout=256, b=2, h=32, w=32, halo=0),
+    "patchgan4x4_s2": dict(ks=4, stride=2, padding=1, cin=154, cout=64, b=2, h=64, w=64, halo=0, act=nhwc.ACT_LRELU),
+    "adaptor3x3_s2": dict(ks=3, stride=2, padding=1, cin=64, cout=128, b=2, h=64, w=64, halo=0),
+    "patchgan4x4_s1_cout1": dict(ks=4, stride=1, padding=1, cin=512, cout=1, b=2, h=31, w=31, halo=0),
+    "patchgan4x4_s1_odd": dict(ks=4, stride=1, padding=1, cin=256, cout=512, b=2, h=32, w=32, halo=0),
+    "split_192": dict(ks=3, stride=1, padding=0, cin=192, cout=192, b=1, h=64, w=64, halo=1, split=True,
+                      out_kind=nhwc.F32),
+    "resblock_407_split": dict(ks=3, stride=1, padding=0, cin=407, cout=407, b=1, h=32, w=32, halo=1, split=True,
+                               out_kind=nhwc.F32),
+    "head_8x8_1024": dict(ks=3, stride=1, padding=0, cin=1024, cout=1024, b=8, h=8, w=8, halo=1),
+    "vgg_conv1_1": dict(ks=3, stride=1, padding=1, cin=3, cout=64, b=2, h=64, w=64, halo=0, act=nhwc.ACT_RELU),
+    "conv_img_tanh": dict(ks=3, stride=1, padding=1, cin=64, cout=3, b=2, h=64, w=64, halo=0, act=nhwc.ACT_TANH,
+                          nchw=True),
+    "ragged_30x30": dict(ks=4, stride=1, padding=1, cin=64, cout=64, b=3, h=31, w=31, halo=0),
+}
+
+
+@pytest.mark.parametrize("name", list(CONV))
+def test_tapconv_forward(name):
+    c = CONV[name]
+    x, wt, bias, _ = make(c)
+
+    def fn(dev):
+        xin = nhwc.pack(x.to(dev), nhwc.F16, pad=c["halo"], split=c.get("split", False))
+        if c.get("nchw"):
+            ho = nhwc.conv_out_size(c["h"] + 2 * c["halo"], c["ks"], c["padding"], c["stride"])
+            wo = nhwc.conv_out_size(c["w"] + 2 * c["halo"], c["ks"], c["padding"], c["stride"])
+            out = torch.zeros(c["b"], c["cout"], ho, wo, device=dev)
+            nhwc.conv(xin, wt.to(dev), bias.to(dev), stride=c["stride"], padding=c["padding"], act=c.get("act", 0),
+                      slope=0.2, nchw_out=out)
+            return (out,)
+        y = nhwc.conv(xin, wt.to(dev), bias.to(dev), stride=c["stride"], padding=c["padding"], act=c.get("act", 0),
+                      slope=0.2, out_kind=c.get("out_kind", nhwc.F16), out_pad=c.get("out_pad", 0),
+                      split_out=bool(c.get("out_pad", 0)))
+        return (y.t,)
+
+    got, want = both(fn)
+    assert got[0].shape == want[0].shape
+    assert rel(got[0], want[0]) < 2e-3
+
+
+def test_tapconv_residual_and_second_launch_reuse():
+    c = dict(ks=3, cin=64, cout=64, b=2, h=32, w=32)
+    x, wt, bias, g = make(c)
+    r = torch.randn(2, 64, 32, 32, generator=g)
+
+    def fn(dev):
+        xin = nhwc.pack(x.to(dev), nhwc.F16)
+        y = nhwc.conv(xin, wt.to(dev), None, padding=1, res=nhwc.pack(r.to(dev), nhwc.F32), out_kind=nhwc.F16)
+        y2 = nhwc.conv(y, wt.to(dev), bias.to(dev), padding=1, res=y, out_kind=nhwc.F32)  # fp16 residual
+        return y.t, y2.t
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 2e-3 and rel(got[1], want[1]) < 2e-3
+
+
+DGRAD = ["spade3x3_halo_n256", "mlp_shared_154", "shortcut1x1", "patchgan4x4_s2", "adaptor3x3_s2", "patchgan4x4_s1_odd",
+         "head_8x8_1024", "ragged_30x30", "conv_img_tanh"]
+
+
+@pytest.mark.parametrize("name", DGRAD)
+def test_tapconv_backward_data(name):
+    c = CONV[name]
+    x, wt, _, g = make(c)
+    hin, win = c["h"] + 2 * c["halo"], c["w"] + 2 * c["halo"]
+    ho, wo = nhwc.conv_out_size(hin, c["ks"], c["padding"], c["stride"]), nhwc.conv_out_size(win, c["ks"], c["padding"],
+                                                                                             c["stride"])
+    gy = torch.randn(c["b"], c["cout"], ho, wo, generator=g)
+    sliced = name == "mlp_shared_154"
+
+    def fn(dev):
+        dy = nhwc.pack(gy.to(dev), nhwc.BF16)
+        dx = nhwc.conv_dgrad(dy, wt.to(dev), (hin, win), stride=c["stride"], padding=c["padding"], in_pad=c["halo"],
+                             c_lo=0, c_n=3 if sliced else None)
+        return (dx.t,)
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 6e-3  # bf16 output
+
+
+WGRAD = ["spade3x3_halo_n256", "mlp_shared_154", "shortcut1x1", "patchgan4x4_s2", "adaptor3x3_s2",
+         "patchgan4x4_s1_cout1", "head_8x8_1024", "vgg_conv1_1", "ragged_30x30", "resblock_407_split", "conv_img_tanh"]
+
+
+@pytest.mark.parametrize("name", WGRAD)
+def test_tapwgrad(name):
+    c = CONV[name]
+    x, wt, _, g = make(c)
+    hin, win = c["h"] + 2 * c["halo"], c["w"] + 2 * c["halo"]
+    ho, wo = nhwc.conv_out_size(hin, c["ks"], c["padding"], c["stride"]), nhwc.conv_out_size(win, c["ks"], c["padding"],
+                                                                                             c["stride"])
+    gy = torch.randn(c["b"], c["cout"], ho, wo, generator=g)
+
+    def fn(dev):
+        xin = nhwc.pack(x.to(dev), nhwc.F16, pad=c["halo"], split=c.get("split", False))
+        dy = nhwc.pack(gy.to(dev), nhwc.BF16)
+        return (nhwc.conv_wgrad(dy, xin, c["ks"], stride=c["stride"], padding=c["padding"]), nhwc.bias_grad(dy))
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 2e-3
+    assert rel(got[1], want[1]) < 1e-4
+
+
+@pytest.mark.parametrize("C,H,W,B,pad,xk,split", [(64, 64, 64, 2, 1, nhwc.F16, False), (1024, 8, 8, 8, 1, nhwc.F16, False),
+                                                    (512, 32, 32, 2, 0, nhwc.F32, False), (256, 16, 16, 2, 1, nhwc.F32, True)])
+def test_spade_mod_nhwc(C, H, W, B, pad, xk, split):
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g) * 2 + 0.3
+    gb = torch.randn(B, 2 * C, H, W, generator=g) * 0.5
+    gy = torch.randn(B, C, H + 2 * pad, W + 2 * pad, generator=g)
+
+    def fn(dev):
+        xn, gn = nhwc.pack(x.to(dev), xk), nhwc.pack(gb.to(dev), xk)
+        y, m, r = nhwc.spade_mod_fwd(xn, gn, C, pad=pad, slope=0.2, split_out=split)
+        dy = nhwc.pack(gy.to(dev), nhwc.BF16)
+        dy.pad = pad
+        dx, dgb = nhwc.spade_mod_bwd(dy, xn, gn, m, r, C, pad, 0.2)
+        dx2, _ = nhwc.spade_mod_bwd(dy, xn, gn, m, r, C, pad, 0.2, dx=nhwc.NT(dx.t.clone(), dx.kind, dx.C))
+        return y.t, m, r, dx.t, dgb.t, dx2.t
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 2e-3
+    assert rel(got[1], want[1]) < 1e-5 and rel(got[2], want[2]) < 1e-5
+    assert rel(got[3], want[3]) < 8e-3 and rel(got[4], want[4]) < 6e-3 and rel(got[5], want[5]) < 1e-2
+
+
+@pytest.mark.parametrize("C,H,W,B,pad,prelu,with_res,xk", [(64, 128, 128, 2, 0, False, False, nhwc.F16),
+                                                           (407, 32, 32, 2, 1, True, True, nhwc.F32),
+                                                           (512, 31, 31, 2, 0, False, False, nhwc.F16)])
+def test_inst_act_nhwc(C, H, W, B, pad, prelu, with_res, xk):
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g) * 1.5 + 0.2
+    res = torch.randn(B, C, H, W, generator=g) if with_res else None
+    gy = torch.randn(B, C, H + 2 * pad, W + 2 * pad, generator=g)
+    gy2 = torch.randn(B, C, H, W, generator=g)
+    a = torch.tensor(0.25)
+
+    def fn(dev):
+        xn = nhwc.pack(x.to(dev), xk)
+        rn = nhwc.pack(res.to(dev), nhwc.F32) if with_res else None
+        st = nhwc.in_stats(xn)
+        aptr = a.to(dev) if prelu else None
+        y, y2 = nhwc.inst_act_fwd(xn, st, slope=0.2, slope_ptr=aptr, res=rn, out_pad=pad, split_out=with_res,
+                                  want_raw=with_res)
+        dy = nhwc.pack(gy.to(dev), nhwc.BF16)
+        dy.pad = pad
+        dslope = torch.zeros((), device=dev) if prelu else None
+        dx, dres = nhwc.inst_act_bwd(dy, xn, st, slope=0.2, slope_ptr=aptr, res=rn,
+                                     dy2=nhwc.pack(gy2.to(dev), nhwc.BF16) if with_res else None, want_dres=with_res,
+                                     dslope=dslope)
+        outs = [st, y.t, dx.t]
+        if with_res:
+            outs += [y2.t, dres.t]
+        if prelu:
+            outs.append(dslope.reshape(1))
+        return tuple(outs)
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 1e-4
+    assert rel(got[1], want[1]) < 2e-3
+    assert rel(got[2], want[2]) < 8e-3
+    for a_, b_ in zip(got[3:], want[3:]):
+        assert rel(a_, b_) < 8e-3
+
+
+def test_pack_unpack_nhwc():
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 154, 64, 64, generator=g)
+
+    def fn(dev):
+        a = nhwc.pack(x.to(dev), nhwc.F16, pad=1, f=4, size=(16, 16))
+        b = nhwc.pack(x.to(dev), nhwc.F16, pad=1, split=True)
+        out = torch.ones(2, 3, 64, 64, device=dev)
+        gsrc = nhwc.pack(x[:, :8, ::4, ::4].contiguous().to(dev), nhwc.BF16, pad=1)
+        nhwc.unpack(gsrc, c_lo=0, C=3, out=out, f=4, acc=True)
+        back = nhwc.unpack(nhwc.pack(x.to(dev), nhwc.F32))
+        return a.t, b.t, out, back
+
+    got, want = both(fn)
+    for a_, b_ in zip(got, want):
+        assert rel(a_, b_) < 1e-6
+    assert torch.equal(got[3].cpu(), x)

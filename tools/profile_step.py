@@ -49,6 +49,36 @@ def main():
     ka = prof.key_averages()
     busy = sum(k.self_device_time_total for k in ka) / 1e3
     print("GPU busy (sum of kernel durations) %.2f ms; launches %d" % (busy, sum(k.count for k in ka if k.self_device_time_total > 0)))
+    # kernel-level list grouped by origin (what share of the GPU-busy time is hand-written?)
+    from torch.autograd import DeviceType
+    rows = [(k.key, k.self_device_time_total / 1e3, k.count) for k in ka
+            if k.self_device_time_total > 0 and k.device_type == DeviceType.CUDA]
+    busy = sum(r[1] for r in rows)
+    print("kernel-only busy %.2f ms over %d launches" % (busy, sum(r[2] for r in rows)))
+    groups = {}
+    def origin(name):
+        if "cocos::" in name:
+            return "cocos (hand-written sm_100a)"
+        if "nchwToNhwc" in name or "nhwcToNchw" in name or "tensorTransform" in name:
+            return "cuDNN layout transposes"
+        if name.startswith("cutlass") or "cudnn" in name or "implicit_convolve" in name or "engines_precompiled" in name \
+                or "dgrad_engine" in name or "wgrad" in name or "xmma" in name or "sm90" in name or "sm100" in name:
+            return "cuDNN / cuBLAS library kernels"
+        if "nccl" in name.lower():
+            return "NCCL"
+        if name.startswith("Memcpy") or name.startswith("Memset"):
+            return "memcpy / memset"
+        return "ATen (at::) elementwise / reduce / other"
+    for name, ms, cnt in rows:
+        g = groups.setdefault(origin(name), [0.0, 0])
+        g[0] += ms
+        g[1] += cnt
+    print("--- share of GPU-busy time by origin ---")
+    for g, (ms, cnt) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
+        print("%6.2f%%  %9.3f ms  x%-6d %s" % (100 * ms / busy, ms, cnt, g))
+    print("--- kernels ---")
+    for name, ms, cnt in sorted(rows, key=lambda r: -r[1])[:args.rows]:
+        print("%6.2f%%  %9.3f ms  x%-5d %s" % (100 * ms / busy, ms, cnt, name[:110]))
     if args.no_table:
         return
     print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=args.rows, max_name_column_width=70))
