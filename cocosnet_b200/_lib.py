@@ -42,6 +42,7 @@ SIGNATURES = {
     "cocos_inst_act_nhwc_bwd": [_vp, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp,
                                 _c_float, _vp, _vp, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                 _c_int, _c_float, _vp],
+    "cocos_act_bwd_nhwc": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int] + [_c_int] * 5 + [_c_float, _vp],
     "cocos_nhwc_pack": [_vp, _vp] + [_c_int] * 11 + [_vp],
     "cocos_nhwc_unpack": [_vp] + [_c_int] * 8 + [_vp] + [_c_int] * 6 + [_vp],
     "cocos_colsum_nhwc": [_vp, _c_int, _c_int, _c_int, _c_ll, _vp, _vp],

@@ -211,6 +211,16 @@ int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* d
                                   H, W, eps, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
+                       int B, int C, int H, int W, int act, float slope, void* stream) {
+  if (!dy || !y || !dz) {
+    set_error("cocos_act_bwd_nhwc: null pointer argument");
+    return -1;
+  }
+  return act_bwd_nhwc_launch(dy, dy_Cs, y, y_kind, y_Cs, pad, dz, dz_Cs, B, C, H, W, act, slope,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
                     int W, int f, int pad, void* stream) {
   if (!src || !dst) {

@@ -87,6 +87,8 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
                              const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
                              int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
                              cudaStream_t stream);
+int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
+                        int B, int C, int H, int W, int act, float slope, cudaStream_t stream);
 int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
                      int W, int f, int pad, cudaStream_t stream);
 int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,

@@ -450,6 +450,32 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const Inst
   }
 }
 
+// ----------------------------------------------------------------------------------------------- activation backward
+// dz = fold_halo(dy) * act'(y) for an activation fused into a convolution epilogue (ReLU / LeakyReLU): y is the op
+// tensor the epilogue wrote (halo `pad`), dy its gradient (bf16, same geometry), dz bf16 without halo.
+__global__ void __launch_bounds__(256)
+act_bwd_nhwc_kernel(const void* __restrict__ dy, int dy_Cs, const void* __restrict__ y, int y_kind, int y_Cs, int pad,
+                    void* __restrict__ dz, int dz_Cs, int B, int C, int H, int W, int act, float slope) {
+  const int n4 = C >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H * W * n4) return;
+  const int c = static_cast<int>(idx % n4) * 4;
+  const long long pixl = idx / n4;
+  const int b = static_cast<int>(pixl / (H * W));
+  const int r = static_cast<int>(pixl - static_cast<long long>(b) * H * W);
+  const int h = r / W, w = r - h * W;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const Fold f = make_fold(h, w, H, W, pad);
+  float4 d = folded4(dy, 2, f, static_cast<size_t>(b) * Hp * Wp, Wp, dy_Cs, c);
+  const float4 v = ld4(y, y_kind, ((static_cast<size_t>(b) * Hp + h + pad) * Wp + w + pad) * y_Cs + c);
+  const float neg = act == 1 ? 0.f : slope;
+  d.x = v.x > 0.f ? d.x : d.x * neg;
+  d.y = v.y > 0.f ? d.y : d.y * neg;
+  d.z = v.z > 0.f ? d.z : d.z * neg;
+  d.w = v.w > 0.f ? d.w : d.w * neg;
+  st4(dz, 2, static_cast<size_t>(pixl) * dz_Cs + c, d);
+}
+
 // ----------------------------------------------------------------------------------------------- pack / unpack
 // fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2p, W+2p, Cs]: dst pixel (h, w) = src pixel (h*f, w*f)
 // (nearest down-sampling by the integer factor f, F.interpolate(mode='nearest')), reflection halo, channels
@@ -701,6 +727,20 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
   COCOS_CUDA_CHECK(cudaGetLastError());
   const long long n = static_cast<long long>(B) * H * W * (C / 4);
   inst_act_nhwc_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
+                        int B, int C, int H, int W, int act, float slope, cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || (C % 4) || (dy_Cs % 4) || (y_Cs % 4) || (dz_Cs % 4) || H <= pad || W <= pad || pad < 0 ||
+      pad > 1 || y_kind < 1 || y_kind > 3 || (act != 1 && act != 2)) {
+    set_error("act_bwd_nhwc: bad arguments (B=%d C=%d H=%d W=%d pad=%d act=%d)", B, C, H, W, pad, act);
+    return -1;
+  }
+  const long long n = static_cast<long long>(B) * H * W * (C / 4);
+  act_bwd_nhwc_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(dy, dy_Cs, y, y_kind, y_Cs, pad, dz, dz_Cs, B, C, H, W,
+                                                              act, slope);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

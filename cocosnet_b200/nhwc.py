@@ -52,15 +52,18 @@ class Group:
         self.dh, self.dw, self.coff, self.r, self.s, self.term = dh, dw, coff, r, s, term
 
 
-def plan_fwd(ks, padding, lo_off=0):
-    """Forward conv (any stride): one group per filter tap, three with 2-term split operands
-    (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo)."""
+def plan_fwd(ks, padding, lo_off=0, wsplit=None):
+    """Forward conv (any stride): one group per filter tap; with 2-term split operands up to three
+    (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo).  lo_off: channel offset of x's lo term (0: x is a single fp16 term);
+    wsplit: also use the lo term of the weights (default: whenever x is split)."""
+    wsplit = bool(lo_off) if wsplit is None else wsplit
     groups = []
     for r in range(ks):
         for s in range(ks):
             groups.append(Group(r - padding, s - padding, 0, r, s, 0))
             if lo_off:
                 groups.append(Group(r - padding, s - padding, lo_off, r, s, 0))
+            if wsplit:
                 groups.append(Group(r - padding, s - padding, 0, r, s, 1))
     return groups
 
@@ -199,6 +202,11 @@ class NativeBackend:
             _p(dres.t if dres else None), dres.Cs if dres else 0, int(dres_acc), x.B, C, x.H, x.W, float(eps),
             _stream()), "cocos_inst_act_nhwc_bwd", kernels=3)
 
+    def act_bwd(self, dy, y, dz, C, act, slope):
+        _lib.check(self.lib.cocos_act_bwd_nhwc(dy.t.data_ptr(), dy.Cs, y.t.data_ptr(), y.kind, y.Cs, y.pad,
+                                               dz.t.data_ptr(), dz.Cs, y.B, C, y.H, y.W, act, float(slope), _stream()),
+                   "cocos_act_bwd_nhwc")
+
     def pack(self, src, dst, C, f):
         b, _, hs, ws = src.shape
         _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, hs, ws,
@@ -275,7 +283,7 @@ def _pack_weight(weight, groups, rows, kc, transposed, bf16):
 
 
 def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kind=F16, out_pad=0, split_out=False,
-         res=None, nchw_out=None, nchw_coff=0):
+         res=None, nchw_out=None, nchw_coff=0, wsplit=None):
     """nn.Conv2d forward on the tap-convolution kernel.  x: NT fp16 (its tensor, halo included, IS the conv input;
     `padding` is the module's zero padding).  Returns an NT of kind out_kind (op tensors: out_pad = 1 adds the
     reflection halo of the next conv, split_out the lo term), or writes fp32 NCHW into `nchw_out` (channels from
@@ -285,7 +293,7 @@ def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out
     assert cin == x.C, (cin, x.C)
     hin, win = x.t.shape[1], x.t.shape[2]
     h, w = conv_out_size(hin, ks, padding, stride), conv_out_size(win, ks, padding, stride)
-    groups = plan_fwd(ks, padding, x.lo)
+    groups = plan_fwd(ks, padding, x.lo, wsplit)
     kchunks = (cin + 63) // 64
     wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False)
     d = dict(B=x.B, Hin=hin, Win=win, Ca=x.Cs, a_stride=stride, bf16=0, H=h, W=w, Cout=cout, w_rows=rows_alloc,
@@ -351,6 +359,14 @@ def bias_grad(dy):
 
 
 # ------------------------------------------------------------------------------------------------ norm / act ops
+def act_bwd(dy, y, act, slope=0.0):
+    """Gradient through a ReLU / LeakyReLU fused into a conv epilogue: dy bf16 and y share the halo; -> bf16, no halo."""
+    assert dy.kind == BF16 and dy.pad == y.pad and act in (ACT_RELU, ACT_LRELU)
+    dz = new(y.B, y.H, y.W, y.C, BF16, y.t.device, zero=False)
+    backend().act_bwd(dy, y, dz, round_up(y.C, 4), act, slope)
+    return dz
+
+
 def spade_mod_fwd(x, gb, C, pad=0, slope=1.0, eps=1e-5, split_out=False):
     """raw x [.., C], raw gb [.., 2C] -> op fp16 (halo pad, lo term) + (mean, rstd) for the backward."""
     assert x.pad == 0 and gb.pad == 0 and x.kind in (F16, F32) and gb.kind in (F16, F32) and gb.C == 2 * C and x.C == C

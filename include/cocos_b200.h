@@ -253,6 +253,12 @@ int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* d
                             int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
                             void* stream);
 
+/* Backward of an activation fused into a cocos_tapconv epilogue (act 1 ReLU: normalization.py:114-117, correspondence.py
+ * 107-146; act 2 LeakyReLU: discriminator.py:93): dz[b,h,w,c] = fold_halo(dy)[b,h,w,c] * act'(y[b,h+pad,w+pad,c]);
+ * dy bf16 and y (kind 1|3) share the halo `pad`; dz bf16 [B,H,W,dz_Cs]. */
+int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
+                       int B, int C, int H, int W, int act, float slope, void* stream);
+
 /* fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2*pad, W+2*pad, Cs]: nearest down-sampling by the integer
  * factor f (F.interpolate(mode='nearest') of normalization.py:130), reflection halo, zero channels [C, Cs) and, for
  * lo_off != 0 (fp16, Cs == 2*lo_off), the lo terms at channel offset lo_off. */

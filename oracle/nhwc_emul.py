@@ -232,6 +232,12 @@ class EmulBackend:
             o2 = dz + (dres.t.float()[..., :C] if dres_acc else 0)
             dres.t[..., :C] = o2.to(dres.t.dtype)
 
+    def act_bwd(self, dy, y, dz, C, act, slope):
+        d = self._fold(dy.t.float()[..., :C], y.pad)
+        p = y.pad
+        v = y.t.float()[:, p:y.t.shape[1] - p, p:y.t.shape[2] - p, :C]
+        dz.t[..., :C] = torch.where(v > 0, d, d * (0.0 if act == 1 else slope)).to(dz.t.dtype)
+
     # ---------------------------------------------------------------------------------------------- pack / unpack
     def pack(self, src, dst, C, f):
         v = src[:, :, ::f, ::f][:, :, :dst.H, :dst.W].permute(0, 2, 3, 1).float()
