@@ -11,6 +11,7 @@ import torch.nn.functional as F
 
 from .. import corr as _corr
 from ..util import feature_normalize, vgg_preprocess
+from . import fast as _fast
 from .blocks import BaseNetwork, conv_apply
 from .generator import AdaptiveFeatureGenerator, DomainClassifier
 
@@ -132,15 +133,20 @@ class NoVGGCorrespondence(BaseNetwork):
         seg = F.interpolate(seg_map, size=feat_seg.shape[2:], mode="nearest")
         ref_seg = F.interpolate(ref_seg_map, size=feat_img.shape[2:], mode="nearest")
         if opt.maskmix:
-            cont = self.layer(torch.cat((feat_seg, seg), 1))
+            cont_in = torch.cat((feat_seg, seg), 1)
             if opt.noise_for_mask and ((not opt.isTrain) or (opt.isTrain and opt.epoch > opt.mask_epoch)):
-                ref = self.layer(torch.cat((feat_img, torch.randn_like(ref_seg) * 0.01), 1))
+                ref_in = torch.cat((feat_img, torch.randn_like(ref_seg) * 0.01), 1)
             else:
-                ref = self.layer(torch.cat((feat_img, ref_seg), 1))
+                ref_in = torch.cat((feat_img, ref_seg), 1)
         else:
-            cont, ref = self.layer(feat_seg), self.layer(feat_img)
-
-        theta, phi = conv_apply(self.theta, cont), conv_apply(self.phi, ref)
+            cont_in, ref_in = feat_seg, feat_img
+        if _fast.resstack_supported(self, cont_in):
+            # both domains as one batch through the shared residual blocks + theta / phi on the NHWC pipeline
+            theta, phi = _fast.resstack_forward(self, cont_in, ref_in,
+                                                precise=getattr(opt, "conv_precision", "split") == "split")
+        else:
+            cont, ref = self.layer(cont_in), self.layer(ref_in)
+            theta, phi = conv_apply(self.theta, cont), conv_apply(self.phi, ref)
         if detach_flag:  # f.detach() at correspondence.py:292-293
             theta, phi = theta.detach(), phi.detach()
         res = _corr.correspondence_tail(

@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fast as _fast
 from .blocks import Attention, BaseNetwork, SPADEResnetBlock, conv_apply, equal_lr, nonspade_norm, norm_act
 
 
@@ -38,6 +39,8 @@ class SPADEGenerator(BaseNetwork):
 
     def forward(self, input, warp_out=None):
         seg = input if warp_out is None else warp_out
+        if _fast.generator_supported(self, seg):  # 16-bit NHWC pipeline, every conv / norm on sm_100a kernels
+            return _fast.generator_forward(self, seg)
         x = conv_apply(self.fc, F.interpolate(seg, size=(self.sh, self.sw)))
         x = self.head_0(x, seg)
         x = self.G_middle_0(self.up(x), seg)
@@ -93,6 +96,8 @@ class AdaptiveFeatureGenerator(BaseNetwork):
                 self.deeper2 = SPADEResnetBlock(4 * nf, 4 * nf, opt)
 
     def forward(self, input, seg):
+        if seg is input and _fast.adaptor_supported(self, input):
+            return _fast.adaptor_forward(self, input, precise=getattr(self.opt, "conv_precision", "split") == "split")
         # layer_{k+1}(actvn(layer_k(.))): the LeakyReLU(0.2) is fused into the norm of the layer that feeds it
         x = input
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):

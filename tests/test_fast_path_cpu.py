@@ -1,0 +1,80 @@
+"""CPU: the 16-bit NHWC tape (cocosnet_b200/tape.py, nets/fast.py) -- generator, domain adaptors, residual stack,
+discriminators, VGG -- driven through the torch emulation of the kernels (oracle/nhwc_emul.py, exact mode) must
+reproduce the goldens minted from the unmodified reference: same losses, outputs and gradient norms as the plain
+host mirror.  This pins the host side of the fast path (tape bookkeeping, hand-written backward chain, weight
+gathering incl. spectral norm) to the reference without a GPU; the kernels are pinned to the emulation on the GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cocosnet_b200 import data as cdata
+from cocosnet_b200 import nhwc
+from cocosnet_b200.options import TrainOptions
+from oracle import torch_port
+from oracle.nhwc_emul import EmulBackend
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ADE_TRAIN = ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+             "--warp_mask_losstype", "direct", "--weight_mask", "100.0", "--vgg_normal_correct", "--batchSize", "1",
+             "--gpu_ids", "-1"]
+
+
+class CountingEmul(EmulBackend):
+    def __init__(self):
+        super().__init__(exact=True)
+        self.calls = {"tapconv": 0, "tapwgrad": 0, "spade_fwd": 0, "inst_fwd": 0}
+
+    def tapconv(self, *a, **k):
+        self.calls["tapconv"] += 1
+        return super().tapconv(*a, **k)
+
+    def tapwgrad(self, *a, **k):
+        self.calls["tapwgrad"] += 1
+        return super().tapwgrad(*a, **k)
+
+    def spade_fwd(self, *a, **k):
+        self.calls["spade_fwd"] += 1
+        return super().spade_fwd(*a, **k)
+
+    def inst_fwd(self, *a, **k):
+        self.calls["inst_fwd"] += 1
+        return super().inst_fwd(*a, **k)
+
+
+@pytest.mark.timeout(1200)
+def test_ade20k_train_step_on_the_tape_matches_reference_golden():
+    from cocosnet_b200.pix2pix_model import Pix2PixModel
+    be = CountingEmul()
+    old = nhwc.set_backend(be)
+    try:
+        gold = np.load(os.path.join(GOLD, "model_ade20k_train.npz"))
+        opt = TrainOptions().parse(ADE_TRAIN, save=False, verbose=False)
+        opt.verbose_networks = False
+        opt.allow_random_vgg = True
+        torch.manual_seed(0)
+        model = Pix2PixModel(opt)
+        model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+        model.train()
+        batch = cdata.synthetic_batch(opt, 1)
+        with torch_port.cpu_reference_mode():
+            g_losses, out = model(batch, mode="generator")
+            sum(g_losses.values()).mean().backward()
+            d_losses = model(batch, mode="discriminator", GforD={"fake_image": out["fake_image"]})
+            sum(d_losses.values()).mean().backward()
+    finally:
+        nhwc.set_backend(old)
+    # the networks really ran on the tape: 3 adaptor passes x (5 + 24) convs, 7 generator blocks, the residual stack ...
+    assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_fwd"] > 30, be.calls
+    for k, v in g_losses.items():
+        assert np.allclose(v.detach().numpy().reshape(-1), gold["g_" + k], rtol=2e-4, atol=1e-6), (k, v, gold["g_" + k])
+    for k, v in d_losses.items():
+        assert np.allclose(v.detach().numpy().reshape(-1), gold["d_" + k], rtol=2e-4), k
+    assert np.allclose(out["fake_image"].detach().numpy()[:, :, ::4, ::4], gold["fake_image_sub"], atol=2e-5)
+    assert np.allclose(out["warp_out"].detach().numpy()[:, :, ::4, ::4], gold["warp_out_sub"], atol=2e-5)
+    for key in gold.files:
+        if key.startswith("gradnorm_"):
+            _, netk, pname = key.split("_", 2)
+            p = dict(model.net[netk].named_parameters())[pname]
+            assert abs(float(p.grad.norm()) - float(gold[key][0])) <= 2e-3 * float(gold[key][0]), key
