@@ -221,13 +221,30 @@ int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int
                              static_cast<cudaStream_t>(stream));
 }
 
-int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
-                    int W, int f, int pad, void* stream) {
+int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
+                    int Hs, int Ws, int H, int W, int f, int pad, void* stream) {
   if (!src || !dst) {
     set_error("cocos_nhwc_pack: null pointer argument");
     return -1;
   }
-  return nhwc_pack_launch(src, dst, kind, B, C, Cs, lo_off, Hs, Ws, H, W, f, pad, static_cast<cudaStream_t>(stream));
+  return nhwc_pack_launch(src, dst, kind, B, C, Cs, lo_off, c_lo, c_span, Hs, Ws, H, W, f, pad,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int cocos_maxpool2_nhwc_fwd(const void* x, void* y, int B, int Cs, int Ho, int Wo, void* stream) {
+  if (!x || !y) {
+    set_error("cocos_maxpool2_nhwc_fwd: null pointer argument");
+    return -1;
+  }
+  return maxpool2_nhwc_fwd_launch(x, y, B, Cs, Ho, Wo, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_maxpool2_nhwc_bwd(const void* dy, const void* x, void* dx, int B, int Cs, int Ho, int Wo, void* stream) {
+  if (!dy || !x || !dx) {
+    set_error("cocos_maxpool2_nhwc_bwd: null pointer argument");
+    return -1;
+  }
+  return maxpool2_nhwc_bwd_launch(dy, x, dx, B, Cs, Ho, Wo, static_cast<cudaStream_t>(stream));
 }
 
 int cocos_nhwc_unpack(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,

@@ -89,8 +89,11 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
                              cudaStream_t stream);
 int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
                         int B, int C, int H, int W, int act, float slope, cudaStream_t stream);
-int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
-                     int W, int f, int pad, cudaStream_t stream);
+int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
+                     int Hs, int Ws, int H, int W, int f, int pad, cudaStream_t stream);
+int maxpool2_nhwc_fwd_launch(const void* x, void* y, int B, int Cs, int Ho, int Wo, cudaStream_t stream);
+int maxpool2_nhwc_bwd_launch(const void* dy, const void* x, void* dx, int B, int Cs, int Ho, int Wo,
+                             cudaStream_t stream);
 int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,
                        int Cd, int cd_lo, int Hd, int Wd, int f, int acc, cudaStream_t stream);
 int colsum_nhwc_launch(const void* x, int kind, int Cs, int C, long long rows, float* out, cudaStream_t stream);

@@ -476,6 +476,74 @@ act_bwd_nhwc_kernel(const void* __restrict__ dy, int dy_Cs, const void* __restri
   st4(dz, 2, static_cast<size_t>(pixl) * dz_Cs + c, d);
 }
 
+// ----------------------------------------------------------------------------------------------- 2x2 max pooling
+// nn.MaxPool2d(kernel_size=2, stride=2) of the VGG19 feature net (correspondence.py:84-100) over fp16 NHWC
+// [B, 2*Ho, 2*Wo, Cs] -> [B, Ho, Wo, Cs]; 8 channels (one 16-byte vector) per thread.
+__global__ void __launch_bounds__(256)
+maxpool2_nhwc_fwd_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int Cs, int Ho, int Wo) {
+  const int n8 = Cs >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Ho * Wo * n8) return;
+  const int c = static_cast<int>(idx % n8) * 8;
+  const long long pix = idx / n8;
+  const int b = static_cast<int>(pix / (Ho * Wo));
+  const int r = static_cast<int>(pix - static_cast<long long>(b) * Ho * Wo);
+  const int ho = r / Wo, wo = r - ho * Wo;
+  const size_t W2 = 2 * static_cast<size_t>(Wo);
+  const size_t base = ((static_cast<size_t>(b) * 2 * Ho + 2 * ho) * W2 + 2 * wo) * Cs + c;
+  const uint4 v00 = *reinterpret_cast<const uint4*>(x + base);
+  const uint4 v01 = *reinterpret_cast<const uint4*>(x + base + Cs);
+  const uint4 v10 = *reinterpret_cast<const uint4*>(x + base + W2 * Cs);
+  const uint4 v11 = *reinterpret_cast<const uint4*>(x + base + W2 * Cs + Cs);
+  uint4 o;
+  const __half2* a = reinterpret_cast<const __half2*>(&v00);
+  const __half2* bb = reinterpret_cast<const __half2*>(&v01);
+  const __half2* cc = reinterpret_cast<const __half2*>(&v10);
+  const __half2* d = reinterpret_cast<const __half2*>(&v11);
+  __half2* oo = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oo[i] = __hmax2(__hmax2(a[i], bb[i]), __hmax2(cc[i], d[i]));
+  *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * Cs + c) = o;
+}
+
+// dx[b, 2ho+i, 2wo+j, c] = dy[b, ho, wo, c] at the FIRST maximum of the window in scan order (what ATen's
+// max_pool2d_with_indices keeps), 0 elsewhere.  x fp16, dy / dx bf16.
+__global__ void __launch_bounds__(256)
+maxpool2_nhwc_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ x, uint16_t* __restrict__ dx,
+                         int B, int Cs, int Ho, int Wo) {
+  const int n8 = Cs >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Ho * Wo * n8) return;
+  const int c = static_cast<int>(idx % n8) * 8;
+  const long long pix = idx / n8;
+  const int b = static_cast<int>(pix / (Ho * Wo));
+  const int r = static_cast<int>(pix - static_cast<long long>(b) * Ho * Wo);
+  const int ho = r / Wo, wo = r - ho * Wo;
+  const size_t W2 = 2 * static_cast<size_t>(Wo);
+  const size_t base = ((static_cast<size_t>(b) * 2 * Ho + 2 * ho) * W2 + 2 * wo) * Cs + c;
+  const size_t off[4] = {0, static_cast<size_t>(Cs), W2 * Cs, W2 * Cs + Cs};
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(x + base + off[k]);
+  const uint4 g = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(pix) * Cs + c);
+  const uint16_t* gs = reinterpret_cast<const uint16_t*>(&g);
+  uint4 o[4];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float best = __half2float(__ushort_as_half(reinterpret_cast<const uint16_t*>(&v[0])[e]));
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float t = __half2float(__ushort_as_half(reinterpret_cast<const uint16_t*>(&v[k])[e]));
+      if (t > best) { best = t; arg = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) reinterpret_cast<uint16_t*>(&o[k])[e] = (k == arg) ? gs[e] : static_cast<uint16_t>(0);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dx + base + off[k]) = o[k];
+}
+
 // ----------------------------------------------------------------------------------------------- pack / unpack
 // fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2p, W+2p, Cs]: dst pixel (h, w) = src pixel (h*f, w*f)
 // (nearest down-sampling by the integer factor f, F.interpolate(mode='nearest')), reflection halo, channels
@@ -745,16 +813,19 @@ int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, in
   return 0;
 }
 
-int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
-                     int W, int f, int pad, cudaStream_t stream) {
+int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
+                     int Hs, int Ws, int H, int W, int f, int pad, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || Cs < C || H <= pad || W <= pad || f < 1 || (H - 1) * f >= Hs || (W - 1) * f >= Ws || pad < 0 ||
-      pad > 1 || kind < 1 || kind > 3 || (lo_off && (kind != 1 || lo_off < C || 2 * lo_off != Cs))) {
-    set_error("nhwc_pack: bad arguments (B=%d C=%d Cs=%d Hs=%d Ws=%d H=%d W=%d f=%d pad=%d)", B, C, Cs, Hs, Ws, H, W, f,
-              pad);
+      pad > 1 || kind < 1 || kind > 3 || (lo_off && (kind != 1 || lo_off < C || 2 * lo_off != Cs)) || c_lo < 0 ||
+      c_span < 0 || (c_span && (c_span < C || c_lo + c_span > (lo_off ? lo_off : Cs)))) {
+    set_error("nhwc_pack: bad arguments (B=%d C=%d Cs=%d c_lo=%d c_span=%d Hs=%d Ws=%d H=%d W=%d f=%d pad=%d)", B, C, Cs,
+              c_lo, c_span, Hs, Ws, H, W, f, pad);
     return -1;
   }
   const int npix = (H + 2 * pad) * (W + 2 * pad);
-  const int cspan = lo_off ? lo_off : Cs;  // channels [cspan, Cs) of a split tensor are written as lo terms
+  // the channel window [c_lo, c_lo + cspan) of dst is written (zeros beyond C); default: everything up to the lo terms
+  const int cspan = c_span ? c_span : (lo_off ? lo_off : Cs) - c_lo;
+  dst = static_cast<char*>(dst) + static_cast<size_t>(c_lo) * (kind == 3 ? 4 : 2);
   dim3 grid((npix + 31) / 32, (cspan + 31) / 32, B);
   nhwc_pack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, dst, kind, C, Cs, cspan, lo_off, Hs, Ws, H, W, f, pad);
   COCOS_CUDA_CHECK(cudaGetLastError());
@@ -771,6 +842,31 @@ int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
   nhwc_unpack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, kind, Cs, c_lo, C, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f,
                                                         acc);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int maxpool2_nhwc_fwd_launch(const void* x, void* y, int B, int Cs, int Ho, int Wo, cudaStream_t stream) {
+  if (B <= 0 || Cs <= 0 || (Cs % 8) || Ho <= 0 || Wo <= 0) {
+    set_error("maxpool2_nhwc_fwd: bad arguments (B=%d Cs=%d Ho=%d Wo=%d)", B, Cs, Ho, Wo);
+    return -1;
+  }
+  const long long n = static_cast<long long>(B) * Ho * Wo * (Cs / 8);
+  maxpool2_nhwc_fwd_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(static_cast<const uint16_t*>(x),
+                                                                   static_cast<uint16_t*>(y), B, Cs, Ho, Wo);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int maxpool2_nhwc_bwd_launch(const void* dy, const void* x, void* dx, int B, int Cs, int Ho, int Wo,
+                             cudaStream_t stream) {
+  if (B <= 0 || Cs <= 0 || (Cs % 8) || Ho <= 0 || Wo <= 0) {
+    set_error("maxpool2_nhwc_bwd: bad arguments (B=%d Cs=%d Ho=%d Wo=%d)", B, Cs, Ho, Wo);
+    return -1;
+  }
+  const long long n = static_cast<long long>(B) * Ho * Wo * (Cs / 8);
+  maxpool2_nhwc_bwd_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(x), static_cast<uint16_t*>(dx), B, Cs, Ho, Wo);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -59,6 +59,8 @@ class VGG19_feature_color_torchversion(nn.Module):
         out = {}
         if preprocess:
             x = vgg_preprocess(x, vgg_normal_correct=self.vgg_normal_correct)
+        if _fast.vgg_supported(self, x):  # conv + ReLU + pooling chain on the 16-bit NHWC tape
+            return _fast.vgg_forward(self, x, out_keys, _VGG_CFG)
         last = max(int(k[1]) for k in out_keys)  # deepest block actually requested
         for name, _, _ in _VGG_CFG:
             blk, idx = int(name[4]), int(name[6])

@@ -284,3 +284,184 @@ def resstack_forward(net, cont, ref, precise=True):
         return [theta, phi]
 
     return T.run(body, [torch.cat((cont, ref), 0)], ps.tensors)
+
+
+# ------------------------------------------------------------------------------------------------ PatchGAN
+def _d_layers(D):
+    """NLayerDiscriminator.model<n> -> [(name, conv, InstanceNorm2d | None, LeakyReLU slope | None)] or None when a
+    layer is not one of the three shapes discriminator.py:92-115 builds."""
+    out = []
+    for name, sub in D.named_children():
+        if "model" not in name:
+            continue
+        if not isinstance(sub, nn.Sequential) or len(sub) not in (1, 2):
+            return None
+        head, slope = sub[0], None
+        if len(sub) == 2:
+            if not isinstance(sub[1], nn.LeakyReLU):
+                return None
+            slope = sub[1].negative_slope
+        norm = None
+        if isinstance(head, nn.Sequential):
+            if len(head) != 2 or not isinstance(head[1], nn.InstanceNorm2d) or head[1].affine \
+                    or head[1].track_running_stats:
+                return None
+            head, norm = head[0], head[1]
+        if not isinstance(head, nn.Conv2d) or head.kernel_size != (4, 4) or head.padding != (1, 1) \
+                or head.stride not in ((1, 1), (2, 2)) or head.dilation != (1, 1) or head.groups != 1 \
+                or head.padding_mode != "zeros" or (norm is not None and slope is None):
+            return None
+        out.append((name, head, norm, slope))
+    return out if out and out[-1][2] is None and out[-1][3] is None else None
+
+
+def discriminator_supported(net, sem, img):
+    ok = enabled() and _dev_ok(sem) and _dev_ok(img) and net.opt.D_cam == 0 and img.shape[1] <= 8 \
+        and sem.shape[2:] == img.shape[2:] and not sem.requires_grad
+    if not ok:
+        return False
+    h, w = img.shape[2:]
+    for _, D in net.named_children():
+        layers = _d_layers(D)
+        if layers is None or (D.use_attn and not any(n == "model3" for n, _, _, _ in layers)):
+            return False
+        hh, ww = h, w
+        for _, conv, _, _ in layers:
+            if conv.stride == (2, 2) and (hh % 2 or ww % 2):
+                return False  # the stride-2 parity view needs even input sizes
+            hh, ww = nhwc.conv_out_size(hh, 4, 1, conv.stride[0]), nhwc.conv_out_size(ww, 4, 1, conv.stride[0])
+            if hh < 1 or ww < 1:
+                return False
+        h, w = (h + 1) // 2, (w + 1) // 2  # the 3x3 / stride-2 average pooling between scales
+    return True
+
+
+def _d_chain(tp, ps, layers, x, emit_all, emit_last=False, first_w=None):
+    """Conv (+ InstanceNorm) (+ LeakyReLU) layers on the tape -> fp32 NCHW outputs: every layer's (emit_all), or only
+    the last one's (emit_last), plus the prediction when the chain ends with it."""
+    outs = []
+    for i, (_, conv, norm, slope) in enumerate(layers):
+        W = first_w if (i == 0 and first_w is not None) else ps.w(conv)
+        stride = conv.stride[0]
+        if slope is None:  # the prediction layer: fp32 NCHW straight from the epilogue
+            outs.append(T.conv(tp, x, W, ps.b(conv), stride=stride, padding=1, nchw=True))
+            return outs
+        if norm is None:
+            x = T.conv(tp, x, W, ps.b(conv), stride=stride, padding=1, act=ACT_LRELU, slope=slope, out_kind=F16)
+        else:
+            r = T.conv(tp, x, W, ps.b(conv), stride=stride, padding=1, out_kind=F16)
+            x, _ = T.inst_act(tp, r, slope=slope, eps=norm.eps, out_kind=F16)
+        if emit_all or (emit_last and i == len(layers) - 1):
+            outs.append(T.unpack_out(tp, x))
+    return outs
+
+
+def discriminator_forward(net, sem, fake, real):
+    """MultiscaleDiscriminator.forward (discriminator.py:56-69) on cat([sem | fake], [sem | real]) -- the batch
+    pix2pix_model.py:299-304 builds -- without building it: returns (pred_fake, pred_real) as divide_pred does
+    (pix2pix_model.py:320-333).  The label map and the two images are packed straight into the fp16 NHWC input of the
+    first 4x4 convolution (image channels first, so every channel window is 16-byte aligned; the filter's input
+    channels are permuted to match).  In the generator step (fake carries a gradient) the fake half is recorded and the
+    real half runs without a tape; in the discriminator step both halves are one batch."""
+    opt = net.opt
+    keep_feats = not opt.no_ganFeat_loss
+    B, ns, ni = sem.shape[0], sem.shape[1], fake.shape[1]
+    need_dx = fake.requires_grad and torch.is_grad_enabled()
+    halves = [(fake, True), (real, False)] if need_dx else [(None, False)]
+    pred = [[] for _ in halves]
+    sem_s, fake_s, real_s = sem, fake, real
+    pool = lambda t: F.avg_pool2d(t, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)  # noqa: E731
+    for si, (_, D) in enumerate(net.named_children()):
+        if si:
+            sem_s, fake_s, real_s = pool(sem_s), pool(fake_s), pool(real_s)
+        layers = _d_layers(D)
+        cut = [n for n, _, _, _ in layers].index("model3") if D.use_attn else len(layers)
+        ps = ParamSet()
+        for _, conv, _, _ in layers:
+            ps.conv(conv)
+        c0 = layers[0][1]
+        # input channels [image | zeros to 8 | label map]
+        w0 = torch.cat((c0.weight[:, ns:ns + ni], c0.weight.new_zeros((c0.out_channels, 8 - ni, 4, 4)), c0.weight[:, :ns]), 1)
+        ps.tensor("w0", w0)
+        H, Wd = sem_s.shape[2:]
+
+        def stage_a(images, grads, record):
+            nb = B * len(images)
+
+            def body(tp, ins, params):
+                ps.bind(params)
+                parts = []
+                for k, g in enumerate(grads):
+                    parts.append((1 + k, ins[1 + k], k * B, 0, 8, g))
+                    parts.append((0, ins[0], k * B, 8, 0, False))
+                x = T.pack_parts(tp, nb, H, Wd, 8 + ns, parts)
+                return _d_chain(tp, ps, layers[:cut], x, keep_feats, emit_last=cut < len(layers), first_w=ps.t("w0"))
+            if record:
+                return list(T.run(body, [sem_s] + images, ps.tensors))
+            with torch.no_grad():
+                return list(T.run(body, [sem_s] + images, ps.tensors))
+
+        def stage_b(x3, record):
+            def body(tp, ins, params):
+                ps.bind(params)
+                x = T.pack_in(tp, 0, ins[0], F16, grad_ch=(0, ins[0].shape[1]))
+                return _d_chain(tp, ps, layers[cut:], x, keep_feats)
+            if record:
+                return list(T.run(body, [x3], ps.tensors))
+            with torch.no_grad():
+                return list(T.run(body, [x3], ps.tensors))
+
+        if need_dx:
+            outs = [stage_a([fake_s], [True], True), stage_a([real_s], [False], False)]
+        else:
+            outs = [stage_a([fake_s, real_s], [False, False], True)]
+        if cut < len(layers):
+            # the SAGAN block in front of model3 (discriminator.py:146-147): ONE call on both halves, so that its
+            # spectral-norm power iterations advance once per forward like the reference's
+            x3 = D.attn(torch.cat([o[-1] for o in outs], 0) if need_dx else outs[0][-1])
+            if need_dx:
+                tails = [stage_b(x3[:B], True), stage_b(x3[B:].detach(), False)]
+            else:
+                tails = [stage_b(x3, True)]
+            outs = [(a if keep_feats else []) + t for a, t in zip(outs, tails)]
+        for k, o in enumerate(outs):
+            pred[k].append(o)
+    if need_dx:
+        return pred[0], pred[1]
+    return ([[t[:B] for t in o] for o in pred[0]], [[t[B:] for t in o] for o in pred[0]])
+
+
+# ------------------------------------------------------------------------------------------------ VGG19 features
+def vgg_supported(net, x):
+    return enabled() and _dev_ok(x) and x.shape[2] % 16 == 0 and x.shape[3] % 16 == 0 \
+        and isinstance(net.pool1, nn.MaxPool2d)
+
+
+def vgg_forward(net, x, out_keys, cfg):
+    """VGG19_feature_color_torchversion.forward (correspondence.py:108-146) after the colour preprocessing: conv +
+    ReLU in one tap-convolution launch each, 2x2 max pooling on fp16 NHWC, the requested relu outputs unpacked to
+    fp32 NCHW for the losses.  cfg: [(attribute name, Cin, Cout)] in network order."""
+    last = max(int(k[1]) for k in out_keys)
+    names = [n for n, _, _ in cfg if int(n[4]) <= last]
+    ps = ParamSet()
+    for n in names:
+        ps.conv(getattr(net, n))
+    need = x.requires_grad and torch.is_grad_enabled()
+
+    def body(tp, ins, params):
+        ps.bind(params)
+        h = T.pack_in(tp, 0, ins[0], F16, grad_ch=(0, ins[0].shape[1]) if need else None)
+        outs = {}
+        for n in names:
+            blk, idx = int(n[4]), int(n[6])
+            c = getattr(net, n)
+            h = T.conv(tp, h, ps.w(c), ps.b(c), padding=1, act=ACT_RELU, out_kind=F16)
+            key = "r%d%d" % (blk, idx)
+            if key in out_keys:
+                outs[key] = T.unpack_out(tp, h)
+            if all(k in outs for k in out_keys):
+                break
+            if idx == (2 if blk <= 2 else 4):
+                h = T.maxpool(tp, h)
+        return [outs[k] for k in out_keys]
+    return list(T.run(body, [x], ps.tensors))

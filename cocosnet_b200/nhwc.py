@@ -207,10 +207,18 @@ class NativeBackend:
                                                dz.t.data_ptr(), dz.Cs, y.B, C, y.H, y.W, act, float(slope), _stream()),
                    "cocos_act_bwd_nhwc")
 
-    def pack(self, src, dst, C, f):
+    def pack(self, src, dst, C, f, c_lo=0, c_span=0):
         b, _, hs, ws = src.shape
-        _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, hs, ws,
-                                            dst.H, dst.W, f, dst.pad, _stream()), "cocos_nhwc_pack")
+        _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, c_lo, c_span,
+                                            hs, ws, dst.H, dst.W, f, dst.pad, _stream()), "cocos_nhwc_pack")
+
+    def maxpool_fwd(self, x, y):
+        _lib.check(self.lib.cocos_maxpool2_nhwc_fwd(x.t.data_ptr(), y.t.data_ptr(), x.B, x.Cs, y.H, y.W, _stream()),
+                   "cocos_maxpool2_nhwc_fwd")
+
+    def maxpool_bwd(self, dy, x, dx):
+        _lib.check(self.lib.cocos_maxpool2_nhwc_bwd(dy.t.data_ptr(), x.t.data_ptr(), dx.t.data_ptr(), x.B, x.Cs, dy.H,
+                                                    dy.W, _stream()), "cocos_maxpool2_nhwc_bwd")
 
     def unpack(self, src, c_lo, C, dst, cd_lo, f, acc):
         _lib.check(self.lib.cocos_nhwc_unpack(src.t.data_ptr(), src.kind, src.Cs, c_lo, C, src.B, src.H, src.W, src.pad,
@@ -261,6 +269,34 @@ def pack(src, kind=F16, pad=0, split=False, f=1, size=None):
     out = new(b, h, w, c, kind, src.device, pad=pad, split=split, zero=False)
     backend().pack(src, out, c, f)
     return out
+
+
+def pack_into(src, dst, b_lo=0, c_lo=0, c_span=0, f=1):
+    """fp32 NCHW `src` -> images [b_lo, b_lo + B) and the channel window [c_lo, c_lo + c_span) of the NT `dst`
+    (zeros beyond src's channels; c_span 0 = all of dst's channels from c_lo)."""
+    src = src.contiguous()
+    b, c = src.shape[:2]
+    view = NT(dst.t[b_lo:b_lo + b], dst.kind, dst.C, dst.pad, dst.lo)
+    backend().pack(src, view, c, f, c_lo, c_span)
+
+
+def batch_view(x, lo, hi):
+    return NT(x.t[lo:hi], x.kind, x.C, x.pad, x.lo)
+
+
+def maxpool2(x):
+    """nn.MaxPool2d(2, 2) of an fp16 NT without halo."""
+    assert x.kind == F16 and x.pad == 0 and x.lo == 0 and x.H % 2 == 0 and x.W % 2 == 0
+    y = NT(backend().empty((x.B, x.H // 2, x.W // 2, x.Cs), F16, x.t.device), F16, x.C)
+    backend().maxpool_fwd(x, y)
+    return y
+
+
+def maxpool2_bwd(dy, x):
+    assert dy.kind == BF16 and dy.pad == 0 and dy.Cs == x.Cs
+    dx = NT(backend().empty(tuple(x.t.shape), BF16, x.t.device), BF16, x.C)
+    backend().maxpool_bwd(dy, x, dx)
+    return dx
 
 
 def unpack(x, c_lo=0, C=None, out=None, cd_lo=0, f=1, acc=False):

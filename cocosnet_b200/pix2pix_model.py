@@ -253,6 +253,11 @@ class Pix2PixModel(torch.nn.Module):
         return {**gen, **coor_out}
 
     def discriminate(self, input_semantics, fake_image, real_image):
+        from .nets import fast as _fast
+        if _fast.discriminator_supported(self.net["netD"], input_semantics, real_image):
+            # [semantics | image] pairs packed straight into the fp16 NHWC input of the PatchGANs (no fp32 concat)
+            pred_fake, pred_real = _fast.discriminator_forward(self.net["netD"], input_semantics, fake_image, real_image)
+            return pred_fake, pred_real, [], None, None
         fake_and_real = torch.cat([torch.cat([input_semantics, fake_image], dim=1),
                                    torch.cat([input_semantics, real_image], dim=1)], dim=0)
         d_out, seg, cam_logit = self.net["netD"](fake_and_real)

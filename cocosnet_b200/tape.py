@@ -98,6 +98,26 @@ def pack_in(tp, index, src, kind=F16, pad=0, split=False, f=1, size=None, grad_c
     return v
 
 
+def pack_parts(tp, B, H, W, C, parts, kind=F16, pad=0):
+    """Several Function inputs -> ONE Var (torch.cat along batch and / or channels without the concatenated fp32
+    tensor).  parts: (index, src fp32 NCHW [b, c, H, W], b_lo, c_lo, c_span, want_grad); the channel windows must
+    cover [0, Cs) of every image."""
+    nt = nhwc.new(B, H, W, C, kind, parts[0][1].device, pad=pad, zero=False)
+    need = False
+    for index, src, b_lo, c_lo, c_span, want in parts:
+        nhwc.pack_into(src, nt, b_lo=b_lo, c_lo=c_lo, c_span=c_span)
+        need = need or (want and tp.record)
+    v = Var(nt, need=need)
+    for index, src, b_lo, c_lo, c_span, want in parts:
+        if want and tp.record:
+            def grad(b_lo=b_lo, c_lo=c_lo, b=src.shape[0], c=src.shape[1]):
+                if v.g is None:
+                    return None
+                return nhwc.unpack(nhwc.batch_view(v.g, b_lo, b_lo + b), c_lo=c_lo, C=c)
+            tp.entries[index] = grad
+    return v
+
+
 def unpack_out(tp, x):
     """Var -> fp32 NCHW Function output."""
     out = nhwc.unpack(x.v)
@@ -215,6 +235,18 @@ def inst_act(tp, x, slope=1.0, prelu=None, res=None, eps=1e-5, out_kind=F16, out
             prelu.add(dslope.reshape(prelu.t.shape))
     tp.add(bwd)
     return out, out2
+
+
+def maxpool(tp, x):
+    """nn.MaxPool2d(2, 2) (the VGG19 feature net, correspondence.py:84-100)."""
+    out = Var(nhwc.maxpool2(x.v), need=x.need)
+
+    def bwd():
+        if out.g is None or not x.need:
+            return
+        acc(x, nhwc.maxpool2_bwd(out.g, x.v))
+    tp.add(bwd)
+    return out
 
 
 def upsample2(tp, x):

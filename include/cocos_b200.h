@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define COCOS_ABI_VERSION 2
+#define COCOS_ABI_VERSION 3
 
 int cocos_abi_version(void);
 const char* cocos_last_error(void);
@@ -261,9 +261,15 @@ int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int
 
 /* fp32 NCHW [B, C, Hs, Ws] -> NHWC kind `kind` [B, H+2*pad, W+2*pad, Cs]: nearest down-sampling by the integer
  * factor f (F.interpolate(mode='nearest') of normalization.py:130), reflection halo, zero channels [C, Cs) and, for
- * lo_off != 0 (fp16, Cs == 2*lo_off), the lo terms at channel offset lo_off. */
-int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int Hs, int Ws, int H,
-                    int W, int f, int pad, void* stream);
+ * lo_off != 0 (fp16, Cs == 2*lo_off), the lo terms at channel offset lo_off.  (c_lo, c_span): the source lands in
+ * the channel window [c_lo, c_lo + c_span) of dst (zeros beyond C; c_span 0 = up to Cs) -- the torch.cat((semantics,
+ * image), 1) of pix2pix_model.py:301-302 without the concatenated tensor. */
+int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
+                    int Hs, int Ws, int H, int W, int f, int pad, void* stream);
+/* nn.MaxPool2d(2, 2) of the VGG19 feature net (correspondence.py:84-100) over fp16 NHWC [B, 2*Ho, 2*Wo, Cs] ->
+ * [B, Ho, Wo, Cs] and its backward (dy / dx bf16, the gradient goes to the first maximum in scan order). */
+int cocos_maxpool2_nhwc_fwd(const void* x, void* y, int B, int Cs, int Ho, int Wo, void* stream);
+int cocos_maxpool2_nhwc_bwd(const void* dy, const void* x, void* dx, int B, int Cs, int Ho, int Wo, void* stream);
 /* NHWC kind `kind` [B, H+2*pad, W+2*pad, Cs], channels [c_lo, c_lo+C), halo folded back -> fp32 NCHW
  * dst[b, cd_lo + c, h*f, w*f] (dst is [B, Cd, Hd, Wd]); acc != 0 adds instead of overwriting. */
 int cocos_nhwc_unpack(const void* src, int kind, int Cs, int c_lo, int C, int B, int H, int W, int pad, float* dst,

@@ -239,15 +239,28 @@ class EmulBackend:
         dz.t[..., :C] = torch.where(v > 0, d, d * (0.0 if act == 1 else slope)).to(dz.t.dtype)
 
     # ---------------------------------------------------------------------------------------------- pack / unpack
-    def pack(self, src, dst, C, f):
+    def pack(self, src, dst, C, f, c_lo=0, c_span=0):
         v = src[:, :, ::f, ::f][:, :, :dst.H, :dst.W].permute(0, 2, 3, 1).float()
-        span = dst.lo if dst.lo else dst.Cs
+        span = c_span if c_span else (dst.lo if dst.lo else dst.Cs) - c_lo
         full = torch.zeros(v.shape[:3] + (span,))
         full[..., :C] = v
         hi = self._round(full, dst.kind)
-        dst.t[..., :span] = self._pad_reflect(hi, dst.pad).to(dst.t.dtype)
+        dst.t[..., c_lo:c_lo + span] = self._pad_reflect(hi, dst.pad).to(dst.t.dtype)
         if dst.lo:
-            dst.t[..., dst.lo:2 * dst.lo] = self._pad_reflect(full - hi, dst.pad).to(dst.t.dtype)
+            dst.t[..., dst.lo + c_lo:dst.lo + c_lo + span] = self._pad_reflect(full - hi, dst.pad).to(dst.t.dtype)
+
+    def maxpool_fwd(self, x, y):
+        B, H, W, Cs = x.t.shape
+        y.t.copy_(x.t.reshape(B, H // 2, 2, W // 2, 2, Cs).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 4, Cs)
+                  .max(3).values)
+
+    def maxpool_bwd(self, dy, x, dx):
+        B, H, W, Cs = x.t.shape
+        win = x.t.float().reshape(B, H // 2, 2, W // 2, 2, Cs).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 4, Cs)
+        mx = win.max(3, keepdim=True).values
+        first = ((win == mx).cumsum(3) == 1) & (win == mx)  # the first maximum in scan order
+        g = first.to(dy.t.dtype) * dy.t[:, :, :, None, :]
+        dx.t.copy_(g.reshape(B, H // 2, W // 2, 2, 2, Cs).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, Cs))
 
     def unpack(self, src, c_lo, C, dst, cd_lo, f, acc):
         v = self._fold(src.t.float()[..., c_lo:c_lo + C], src.pad).permute(0, 3, 1, 2)

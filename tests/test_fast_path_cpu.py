@@ -24,10 +24,20 @@ ADE_TRAIN = ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO
 class CountingEmul(EmulBackend):
     def __init__(self):
         super().__init__(exact=True)
-        self.calls = {"tapconv": 0, "tapwgrad": 0, "spade_fwd": 0, "inst_fwd": 0}
+        self.calls = {"tapconv": 0, "tapwgrad": 0, "spade_fwd": 0, "inst_fwd": 0, "maxpool_fwd": 0, "maxpool_bwd": 0,
+                      "stride2": 0}
+
+    def maxpool_fwd(self, *a, **k):
+        self.calls["maxpool_fwd"] += 1
+        return super().maxpool_fwd(*a, **k)
+
+    def maxpool_bwd(self, *a, **k):
+        self.calls["maxpool_bwd"] += 1
+        return super().maxpool_bwd(*a, **k)
 
     def tapconv(self, *a, **k):
         self.calls["tapconv"] += 1
+        self.calls["stride2"] += int(a[5]["a_stride"] == 2 and len(a[5]["groups"]) == 16)  # PatchGAN 4x4 / stride 2
         return super().tapconv(*a, **k)
 
     def tapwgrad(self, *a, **k):
@@ -67,6 +77,9 @@ def test_ade20k_train_step_on_the_tape_matches_reference_golden():
         nhwc.set_backend(old)
     # the networks really ran on the tape: 3 adaptor passes x (5 + 24) convs, 7 generator blocks, the residual stack ...
     assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_fwd"] > 30, be.calls
+    # ... the VGG19 feature net (3 forward passes x 4 poolings, one backward) and both PatchGANs (3 stride-2 4x4
+    # convolutions each, G step: fake + real halves, D step: one batch)
+    assert be.calls["maxpool_fwd"] == 12 and be.calls["maxpool_bwd"] == 4 and be.calls["stride2"] >= 18, be.calls
     for k, v in g_losses.items():
         assert np.allclose(v.detach().numpy().reshape(-1), gold["g_" + k], rtol=2e-4, atol=1e-6), (k, v, gold["g_" + k])
     for k, v in d_losses.items():

@@ -226,3 +226,46 @@ def test_pack_unpack_nhwc():
     for a_, b_ in zip(got, want):
         assert rel(a_, b_) < 1e-6
     assert torch.equal(got[3].cpu(), x)
+
+
+def test_pack_into_channel_windows_and_batch_halves():
+    """[image | zeros | label map] x [fake ; real] assembled by four window packs == torch.cat of the fp32 tensors."""
+    g = torch.Generator().manual_seed(11)
+    sem = (torch.rand(2, 151, 32, 32, generator=g) > 0.9).float()
+    fake, real = torch.randn(2, 3, 32, 32, generator=g), torch.randn(2, 3, 32, 32, generator=g)
+
+    def fn(dev):
+        nt = nhwc.new(4, 32, 32, 159, nhwc.F16, dev, zero=False)
+        for k, img in enumerate((fake, real)):
+            nhwc.pack_into(img.to(dev), nt, b_lo=2 * k, c_lo=0, c_span=8)
+            nhwc.pack_into(sem.to(dev), nt, b_lo=2 * k, c_lo=8)
+        return (nt.t,)
+
+    got, want = both(fn)
+    assert torch.equal(got[0].cpu().float(), want[0].float())
+    z5, z1 = torch.zeros(2, 5, 32, 32), torch.zeros(2, 1, 32, 32)  # Cs = 160: one padding channel after the label map
+    full = torch.cat((torch.cat((fake, z5, sem, z1), 1), torch.cat((real, z5, sem, z1), 1)), 0)
+    assert torch.equal(got[0].cpu().float(), full.permute(0, 2, 3, 1).half().float())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 64, 64), (3, 512, 16, 16), (1, 128, 6, 10)])
+def test_maxpool2_nhwc(B, C, H, W):
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, C, H, W, generator=g).relu()  # post-ReLU: windows of tied zeros exercise the first-max rule
+    dy = torch.randn(B, C, H // 2, W // 2, generator=g)
+
+    def fn(dev):
+        xin = nhwc.pack(x.to(dev), nhwc.F16)
+        y = nhwc.maxpool2(xin)
+        dx = nhwc.maxpool2_bwd(nhwc.pack(dy.to(dev), nhwc.BF16), xin)
+        return y.t, dx.t
+
+    got, want = both(fn)
+    assert torch.equal(got[0].cpu().float(), want[0].float())
+    assert torch.equal(got[1].cpu().float(), want[1].float())
+    # and the emulation is ATen's max_pool2d + its backward on the same rounded values
+    xr = x.half().float().requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(xr, 2, 2)
+    yr.backward(dy.bfloat16().float())
+    assert torch.equal(want[0].float().permute(0, 3, 1, 2), yr.detach())
+    assert torch.equal(want[1].float().permute(0, 3, 1, 2), xr.grad)
