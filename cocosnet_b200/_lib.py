@@ -26,7 +26,9 @@ SIGNATURES = {
     "cocos_conv_wgrad": [_vp, _vp, _vp] + [_c_int] * 12 + [_vp],
     "cocos_cast_taps": [_vp, _vp, ctypes.c_longlong] + [_c_int] * 7 + [_vp],
     "cocos_conv_fwd": [_vp, _vp, _vp, _vp] + [_c_int] * 10 + [_vp],
-    "cocos_normalize_pack": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp],
+    "cocos_normalize_pack": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp],
+    "cocos_normalize_pack_bwd": [_vp] * 7 + [_c_int] * 5 + [_vp],
+    "cocos_transpose_f16_bf16": [_vp, _vp, _c_int, _c_int, _c_int, _vp],
     "cocos_inst_act_fwd": [_vp] * 4 + [_c_int, _c_int, _c_float, _c_float, _vp],
     "cocos_inst_act_bwd": [_vp] * 5 + [_c_int, _c_int, _c_float, _vp],
     "cocos_tapconv": [_vp, _vp],

@@ -57,15 +57,91 @@ class _Attend(torch.autograd.Function):
 
 
 class Packed:
-    """fp16 K-major operand [B,N,Kd] produced by the fused prologue (no autograd graph behind it)."""
+    """fp16 K-major operand [B,N,Kd] produced by the fused prologue.  Without autograd: just the tensor.  With
+    autograd: `token` (a 1-element fp32 tensor, the autograd handle of the operand) and `holder` (the operand's
+    state: packed tensor, per-position statistics, and the fp32 gradient accumulator the attend backwards add into)."""
 
-    def __init__(self, t):
-        self.t = t
+    def __init__(self, t, token=None, holder=None):
+        self.t, self.token, self.holder = t, token, holder
+
+
+class _Holder:
+    __slots__ = ("q16", "g", "cm")
+
+    def __init__(self):
+        self.q16 = self.g = self.cm = None
+
+    def channel_major(self):
+        """bf16 [B, K, N] copy of the operand: the A operand of the dQ / dK GEMMs (made once per backward)."""
+        if self.cm is None:
+            self.cm = ops.transpose_rows_bf16(self.q16)
+        return self.cm
+
+
+class _Operand(torch.autograd.Function):
+    """theta / phi conv output -> normalised fp16 operand (correspondence.py:273-289, --PONO_C) with autograd.
+    autograd insists that a gradient has the dtype of its tensor, and the operand is fp16 while its gradient must
+    be fp32, so the operand itself travels in `holder` and the Function returns a 1-element fp32 TOKEN: every
+    attend that uses the operand takes the token as an input and adds its dL/d(operand) into holder.g; the engine
+    runs this backward after all of them, where the whole normalise / centre / unfold chain is two kernels."""
+
+    @staticmethod
+    def forward(ctx, x, match_kernel, holder):
+        x = x.contiguous()
+        holder.q16, mean, inv = ops.normalize_pack(x, match_kernel, _EPS, stats=True)
+        ctx.save_for_backward(x, mean, inv)
+        ctx.holder, ctx.mk = holder, match_kernel
+        return x.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, _gtoken):
+        x, mean, inv = ctx.saved_tensors
+        h = ctx.holder
+        g, h.g, h.cm = h.g, None, None
+        if g is None:
+            return torch.zeros_like(x), None, None
+        return ops.normalize_pack_bwd(g, x, mean, inv, ctx.mk), None, None
+
+
+class _AttendPacked(torch.autograd.Function):
+    """softmax(scale * Q K^T) V on packed operands (see _Operand); v [B,Cv,Nk] fp32 -> [B,Cv,Nq]."""
+
+    @staticmethod
+    def forward(ctx, tq, tk, v, hq, hk, scale):
+        v = v.contiguous()
+        nk = hk.q16.shape[1]
+        if v.shape[1] <= 4 and nk % 4 == 0:
+            out, lse, _ = ops.corr_warp_fwd(hq.q16, hk.q16, None, v.shape[1], nk, scale, want_lse=True, v32=v)
+        else:
+            out, lse, _ = ops.corr_warp_fwd(hq.q16, hk.q16, ops.pack_v(v), v.shape[1], nk, scale, want_lse=True)
+        ctx.save_for_backward(v, out, lse)
+        ctx.hq, ctx.hk, ctx.scale = hq, hk, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        v, out, lse = ctx.saved_tensors
+        hq, hk = ctx.hq, ctx.hk
+        need_q, need_k, need_v = ctx.needs_input_grad[:3]
+        cv = v.shape[1]
+        cvk = ops.round_up(cv, 64)
+        do16, rscale = ops.pack_rows(d_out.contiguous(), kp=cvk, rowscale=True)
+        v16 = ops.pack_rows(v, kp=cvk)
+        ds, dst, pt = ops.corr_warp_bwd_ds(hq.q16, hk.q16, do16, rscale, v16, out, lse, cv, ctx.scale, need_v)
+        if need_q:  # dL/dQhat^T [B,Kd,Nq] = Khat_cm . dS, summed over every attend that used the operand
+            hq.g = ops.gemm_f16(hk.channel_major(), ds, out=hq.g, accumulate=hq.g is not None)
+        if need_k:
+            hk.g = ops.gemm_f16(hq.channel_major(), dst, out=hk.g, accumulate=hk.g is not None)
+        dv = ops.gemm_f16(ops.cast_rows(d_out.contiguous(), torch.bfloat16), pt) if need_v else None
+        zero = lambda need: d_out.new_zeros(1) if need else None  # noqa: E731
+        return zero(need_q), zero(need_k), dv, None, None, None
 
 
 def attend(q, k, v, scale, precision="fp16"):
     """q [B,Kd,Nq], k [B,Kd,Nk], v [B,Cv,Nk] fp32 CUDA -> [B,Cv,Nq].  q / k may also be `Packed` operands
     (inference path): forward only."""
+    if isinstance(q, Packed) and q.holder is not None:
+        return _AttendPacked.apply(q.token, k.token, v, q.holder, k.holder, float(scale))
     if isinstance(q, Packed):
         v = v.contiguous()
         nk = k.t.shape[1]
@@ -82,14 +158,24 @@ def raw_correlation(q, k, scale):
     return ops.gemm_f16(q16, k16, alpha=scale)
 
 
-def _operands(x, match_kernel, pono_c, precision):
+import os as _os
+
+# train path: unfold / centre / normalise + its backward as fused kernels (COCOS_FUSED_PROLOGUE=0: torch ops, A/B runs)
+FUSED_PROLOGUE = _os.environ.get("COCOS_FUSED_PROLOGUE", "1") != "0"
+
+
+def _operands(x, match_kernel, pono_c, precision, with_grad_ok=True):
     """theta / phi conv output -> normalised correlation operand.  Without autograd (inference) and with
     --PONO_C the whole prologue (unfold, centre, normalise, fp16 pack) is one fused kernel pair."""
-    fused = (not (torch.is_grad_enabled() and x.requires_grad)) and pono_c and precision == "fp16" \
+    fused = pono_c and precision == "fp16" \
         and match_kernel in (1, 3) and x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0 \
         and (x.shape[1] * match_kernel * match_kernel) % 64 == 0
-    if fused:
+    if fused and not (torch.is_grad_enabled() and x.requires_grad):
         return Packed(ops.normalize_pack(x, match_kernel, _EPS))
+    if fused and with_grad_ok and FUSED_PROLOGUE:
+        holder = _Holder()
+        token = _Operand.apply(x, match_kernel, holder)
+        return Packed(holder.q16, token, holder)
     return _unfold_center_normalize(x, match_kernel, pono_c)
 
 
@@ -101,9 +187,17 @@ def correspondence_tail(theta_conv, phi_conv, ref_img, *, match_kernel=3, pono_c
     [B,3,h,w] (or folded [B,3,256,256] for warp_patch); extras holds
     warp_mask / warp_cycle / warp_i2r / warp_i2r2i when requested."""
     b, _, fh, fw = theta_conv.shape
-    theta = _operands(theta_conv, match_kernel, pono_c, precision)
-    phi = _operands(phi_conv, match_kernel, pono_c, precision)
-    if isinstance(theta, Packed) != isinstance(phi, Packed):  # keep the two operands in the same K order
+    if precision == "auto":
+        # operand rounding (2^-11 per element) reaches the logits as 100 * 2^-11 * O(1/sqrt(K)): single fp16 terms meet
+        # the 1e-3 bar on warp_out at K = 2304 (6e-4) but not at K = 256 (1.0e-3, profiles/r02_parity_split_c4.txt)
+        precision = "split" if theta_conv.shape[1] * match_kernel * match_kernel < 1024 else "fp16"
+    # the two operands must be of the same kind (same K order; the packed attend needs both holders)
+    both_grad = torch.is_grad_enabled() and theta_conv.requires_grad and phi_conv.requires_grad
+    none_grad = not (torch.is_grad_enabled() and (theta_conv.requires_grad or phi_conv.requires_grad))
+    theta = _operands(theta_conv, match_kernel, pono_c, precision, with_grad_ok=both_grad)
+    phi = _operands(phi_conv, match_kernel, pono_c, precision, with_grad_ok=both_grad)
+    if (isinstance(theta, Packed) != isinstance(phi, Packed)) or \
+            (isinstance(theta, Packed) and not (both_grad or none_grad)):
         theta = _unfold_center_normalize(theta_conv, match_kernel, pono_c)
         phi = _unfold_center_normalize(phi_conv, match_kernel, pono_c)
     scale = 1.0 / temperature

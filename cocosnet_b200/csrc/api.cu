@@ -92,13 +92,32 @@ int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const
   return inst_act_bwd_launch(dy, x, mean, rstd, dx, planes, HW, slope, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int match_kernel,
-                         float eps, void* stream) {
+int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, float* mean_out, float* inv_out, int B, int C,
+                         int h, int w, int match_kernel, float eps, void* stream) {
   if (!x || !xt_workspace || !out) {
     set_error("cocos_normalize_pack: null pointer argument");
     return -1;
   }
-  return norm_pack_launch(x, xt_workspace, out, B, C, h, w, match_kernel, eps, static_cast<cudaStream_t>(stream));
+  return norm_pack_launch(x, xt_workspace, out, mean_out, inv_out, B, C, h, w, match_kernel, eps,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int cocos_normalize_pack_bwd(const float* g, const float* x, const float* mean, const float* inv, float* a_ws,
+                             float* s_ws, float* dx, int B, int C, int h, int w, int match_kernel, void* stream) {
+  if (!g || !x || !mean || !inv || !a_ws || !s_ws || !dx) {
+    set_error("cocos_normalize_pack_bwd: null pointer argument");
+    return -1;
+  }
+  return norm_pack_bwd_launch(g, x, mean, inv, a_ws, s_ws, dx, B, C, h, w, match_kernel,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int cocos_transpose_f16_bf16(const void* src, void* dst, int B, int N, int K, void* stream) {
+  if (!src || !dst) {
+    set_error("cocos_transpose_f16_bf16: null pointer argument");
+    return -1;
+  }
+  return transpose_f16_bf16_launch(src, dst, B, N, K, static_cast<cudaStream_t>(stream));
 }
 
 int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,

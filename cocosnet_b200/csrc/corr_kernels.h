@@ -47,8 +47,11 @@ int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, in
 int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
                     int Cp, int Cout, int KS, int off, int bf16, cudaStream_t stream);
 
-int norm_pack_launch(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int mk, float eps,
-                     cudaStream_t stream);
+int norm_pack_launch(const float* x, float* xt_workspace, void* out, float* mean_out, float* inv_out, int B, int C, int h,
+                     int w, int mk, float eps, cudaStream_t stream);
+int norm_pack_bwd_launch(const float* g, const float* x, const float* mean, const float* inv, float* a_ws, float* s_ws,
+                         float* dx, int B, int C, int h, int w, int mk, cudaStream_t stream);
+int transpose_f16_bf16_launch(const void* src, void* dst, int B, int N, int K, cudaStream_t stream);
 
 int inst_act_fwd_launch(const float* x, float* y, float* mean, float* rstd, int planes, int HW, float slope, float eps,
                         cudaStream_t stream);

@@ -56,8 +56,13 @@ def synthetic_batch(opt, batch, seed=1234, pin=False):
     return out
 
 
-def create_dataloader(opt):
+def create_dataloader(opt, seed=0):
+    """Global batches of opt.batchSize (data/__init__.py:40-60).  The shuffle order comes from a generator seeded
+    identically on every rank, so with one process per GPU all ranks draw the SAME global batch and
+    trainer.shard_batch() hands each its contiguous slice -- DataParallel.scatter's split of one batch."""
     ds = SyntheticDataset(opt)
     print("dataset [%s] of size %d was created" % (type(ds).__name__, len(ds)))
+    gen = torch.Generator()
+    gen.manual_seed(seed)
     return torch.utils.data.DataLoader(ds, batch_size=opt.batchSize, shuffle=not opt.serial_batches,
-                                       num_workers=0, drop_last=opt.isTrain)
+                                       num_workers=0, drop_last=opt.isTrain, generator=gen)

@@ -17,11 +17,38 @@ from .. import corr as _corr
 from .. import ops as _ops
 
 
+_STRICT = [0]  # > 0: inside strict_convs()
+
+
+class strict_convs:
+    """Context for the layers that have no kernel on the NHWC pipeline yet (SPADE with batch / instance statistics:
+    the celebahq / deepfashion configs) when the 1e-3 parity mode is on (--conv_precision split): their convolutions
+    run in plain fp32 (cuDNN, TF32 off) instead of single-term fp16 / TF32, whose rounding the correlation's
+    1/temperature = 100 amplifies to 5e-3 on warp_out (profiles/r02_parity_*.txt)."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        if self.on:
+            _STRICT[0] += 1
+            self._flags = torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                                     deterministic=torch.backends.cudnn.deterministic, allow_tf32=False)
+            self._flags.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self._flags.__exit__(*exc)
+            _STRICT[0] -= 1
+        return False
+
+
 def conv_apply(conv, x):
     """`conv(x)` for an nn.Conv2d (possibly wrapped by spectral_norm / equal_lr): stride-1 3x3 / 1x1 convolutions
     run their forward on the tcgen05 implicit-GEMM kernel (K2, fp16 operands / fp32 accumulate, TF32-class
     precision); anything else, or `COCOS_NATIVE_CONV=0`, falls back to the module (cuDNN)."""
-    if (_ops.NATIVE_CONV and isinstance(conv, nn.Conv2d) and x.is_cuda and x.dtype == torch.float32
+    if (_ops.NATIVE_CONV and not _STRICT[0] and isinstance(conv, nn.Conv2d) and x.is_cuda and x.dtype == torch.float32
             and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.kernel_size in ((3, 3), (1, 1)) and conv.padding_mode == "zeros"
             and conv.padding in ((0, 0), (conv.kernel_size[0] // 2,) * 2) and conv.out_channels >= 16):
@@ -179,7 +206,7 @@ class SPADE(nn.Module):
         b = torch.cat((self.mlp_gamma.bias, self.mlp_beta.bias), 0)
         if actv.dim() == 4 and actv.is_contiguous(memory_format=torch.channels_last) and not actv.is_contiguous():
             return F.conv2d(actv, w.contiguous(memory_format=torch.channels_last), b)
-        if _ops.NATIVE_CONV and actv.is_cuda and actv.dtype == torch.float32 and w.shape[2] in (1, 3):
+        if _ops.NATIVE_CONV and not _STRICT[0] and actv.is_cuda and actv.dtype == torch.float32 and w.shape[2] in (1, 3):
             return _ops.conv_native(actv, w, b, pre_padded=True)
         return F.conv2d(actv, w, b)
 

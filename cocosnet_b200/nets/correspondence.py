@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from .. import corr as _corr
 from ..util import feature_normalize, vgg_preprocess
 from . import fast as _fast
-from .blocks import BaseNetwork, conv_apply
+from .blocks import BaseNetwork, conv_apply, strict_convs
 from .generator import AdaptiveFeatureGenerator, DomainClassifier
 
 
@@ -145,10 +145,11 @@ class NoVGGCorrespondence(BaseNetwork):
         if _fast.resstack_supported(self, cont_in):
             # both domains as one batch through the shared residual blocks + theta / phi on the NHWC pipeline
             theta, phi = _fast.resstack_forward(self, cont_in, ref_in,
-                                                precise=getattr(opt, "conv_precision", "split") == "split")
+                                                precise=_fast.conv_precision(opt) != "fast")
         else:
-            cont, ref = self.layer(cont_in), self.layer(ref_in)
-            theta, phi = conv_apply(self.theta, cont), conv_apply(self.phi, ref)
+            with strict_convs(cont_in.is_cuda and _fast.conv_precision(opt) != "fast"):
+                cont, ref = self.layer(cont_in), self.layer(ref_in)
+                theta, phi = conv_apply(self.theta, cont), conv_apply(self.phi, ref)
         if detach_flag:  # f.detach() at correspondence.py:292-293
             theta, phi = theta.detach(), phi.detach()
         res = _corr.correspondence_tail(
@@ -156,7 +157,7 @@ class NoVGGCorrespondence(BaseNetwork):
             down=opt.down, warp_patch=opt.warp_patch, ref_seg_map=ref_seg_map, seg_map=seg_map, real_img=real_img,
             warp_mask_losstype=opt.warp_mask_losstype, show_warpmask=opt.show_warpmask,
             warp_cycle=opt.warp_cycle_w > 0, two_cycle=opt.two_cycle, return_corr=return_corr,
-            precision=getattr(opt, "corr_precision", "fp16"))
+            precision=getattr(opt, "corr_precision", "auto"))
         if return_corr:
             return res[0]
         y, extras = res

@@ -126,9 +126,10 @@ def spade_norm(tp, ps, norm, x, pyr, mode, slope, pad):
     return T.spade(tp, x, gb, C, pad, slope, mode.split)
 
 
-def spade_block(tp, ps, blk, x, pyr, mode, final_act=ACT_NONE, final_slope=0.0):
+def spade_block(tp, ps, blk, x, pyr, mode, final_act=ACT_NONE, final_slope=0.0, final_op=False):
     """SPADEResnetBlock.forward (architecture.py:70-95); the residual sum (and, for the generator's last block, the
-    LeakyReLU in front of conv_img) ride in conv_1's epilogue."""
+    LeakyReLU in front of conv_img) ride in conv_1's epilogue.  final_op: the result is the operand of the next
+    convolution (fp16, lo term in split mode) instead of a raw activation."""
     if blk.learned_shortcut:
         xs = T.conv(tp, spade_norm(tp, ps, blk.norm_s, x, pyr, mode, 1.0, 0), ps.w(blk.conv_s), None, out_kind=mode.raw)
     else:
@@ -136,7 +137,8 @@ def spade_block(tp, ps, blk, x, pyr, mode, final_act=ACT_NONE, final_slope=0.0):
     h = T.conv(tp, spade_norm(tp, ps, blk.norm_0, x, pyr, mode, 0.2, 1), ps.w(blk.conv_0), ps.b(blk.conv_0),
                out_kind=mode.raw)
     return T.conv(tp, spade_norm(tp, ps, blk.norm_1, h, pyr, mode, 0.2, 1), ps.w(blk.conv_1), ps.b(blk.conv_1),
-                  out_kind=mode.raw, res=xs, act=final_act, slope=final_slope)
+                  out_kind=F16 if final_op else mode.raw, split_out=final_op and mode.split, res=xs, act=final_act,
+                  slope=final_slope)
 
 
 # ------------------------------------------------------------------------------------------------ SPADE generator
@@ -146,27 +148,40 @@ def generator_supported(net, seg):
         and seg.shape[2] % 32 == 0 and net.sh == net.sw and isinstance(net.fc, nn.Conv2d)
 
 
+def conv_precision(opt):
+    """'split': every convolution upstream of an output the parity bar covers (warp_out AND fake_image) runs on
+    2-term fp16 split operands with fp32 activations in between; 'mixed': only the correspondence path (where
+    1/temperature = 100 amplifies every rounding error), the generator on single fp16 terms; 'fast': single terms
+    everywhere.  COCOS_CONV_PRECISION overrides the option (A/B runs)."""
+    import os
+    return os.environ.get("COCOS_CONV_PRECISION") or getattr(opt, "conv_precision", "split")
+
+
 def generator_forward(net, seg):
     """SPADEGenerator.forward (generator.py:60-89).  seg = cat(warp_out, semantics) fp32 NCHW."""
     opt = net.opt
+    mode = T.PRECISE if conv_precision(opt) == "split" else T.FAST
     grad_ch = (0, 3) if ("warp" in opt.CBN_intype and seg.requires_grad) else None
     first = [net.head_0, net.G_middle_0, net.G_middle_1, net.up_0, net.up_1]
     last = [net.up_2, net.up_3]
 
     def stage_a(tp, ps, pyr):
-        x = T.conv(tp, pyr.get(net.sh, net.sw, 0), ps.w(net.fc), ps.b(net.fc), padding=1, out_kind=F16, dx_ch=grad_ch)
-        x = spade_block(tp, ps, net.head_0, x, pyr, T.FAST)
-        x = spade_block(tp, ps, net.G_middle_0, T.upsample2(tp, x), pyr, T.FAST)
-        x = spade_block(tp, ps, net.G_middle_1, x, pyr, T.FAST)
-        x = spade_block(tp, ps, net.up_0, T.upsample2(tp, x), pyr, T.FAST)
-        x = spade_block(tp, ps, net.up_1, T.upsample2(tp, x), pyr, T.FAST)
+        x = T.conv(tp, pyr.get(net.sh, net.sw, 0), ps.w(net.fc), ps.b(net.fc), padding=1, out_kind=mode.raw,
+                   dx_ch=grad_ch, wsplit=mode.split)
+        x = spade_block(tp, ps, net.head_0, x, pyr, mode)
+        x = spade_block(tp, ps, net.G_middle_0, T.upsample2(tp, x), pyr, mode)
+        x = spade_block(tp, ps, net.G_middle_1, x, pyr, mode)
+        x = spade_block(tp, ps, net.up_0, T.upsample2(tp, x), pyr, mode)
+        x = spade_block(tp, ps, net.up_1, T.upsample2(tp, x), pyr, mode)
         return T.upsample2(tp, x)
 
     def stage_b(tp, ps, pyr, x):
-        x = spade_block(tp, ps, net.up_2, x, pyr, T.FAST)
+        x = spade_block(tp, ps, net.up_2, x, pyr, mode)
         # up_3 + leaky_relu(0.2) (generator.py:87) in its conv_1 epilogue, then conv_img + tanh -> fp32 NCHW
-        x = spade_block(tp, ps, net.up_3, T.upsample2(tp, x), pyr, T.FAST, final_act=ACT_LRELU, final_slope=0.2)
-        return T.conv(tp, x, ps.w(net.conv_img), ps.b(net.conv_img), padding=1, act=ACT_TANH, nchw=True)
+        x = spade_block(tp, ps, net.up_3, T.upsample2(tp, x), pyr, mode, final_act=ACT_LRELU, final_slope=0.2,
+                        final_op=True)
+        return T.conv(tp, x, ps.w(net.conv_img), ps.b(net.conv_img), padding=1, act=ACT_TANH, nchw=True,
+                      wsplit=mode.split)
 
     def run_stage(blocks, extra_convs, fn, inputs):
         ps = ParamSet()
@@ -177,7 +192,9 @@ def generator_forward(net, seg):
 
         def body(tp, ins, params):
             ps.bind(params)
-            pyr = Pyramid(tp, 0, ins[0], grad_ch, False)
+            # the condition = [warped exemplar (fp32 values) | one-hot label map]: the lo term only matters for the
+            # image channels, but a split operand carries it for all of them
+            pyr = Pyramid(tp, 0, ins[0], grad_ch, mode.split and "warp" in opt.CBN_intype)
             return fn(tp, ps, pyr, ins)
         return T.run(body, inputs, ps.tensors)
 
@@ -187,7 +204,8 @@ def generator_forward(net, seg):
     mid = run_stage(first, [net.fc], lambda tp, ps, pyr, ins: [T.unpack_out(tp, stage_a(tp, ps, pyr))], [seg])[0]
     mid = net.attn(mid)
     return run_stage(last, [net.conv_img],
-                     lambda tp, ps, pyr, ins: [stage_b(tp, ps, pyr, T.pack_in(tp, 1, ins[1], F16, grad_ch=(0, ins[1].shape[1])))],
+                     lambda tp, ps, pyr, ins: [stage_b(tp, ps, pyr, T.pack_in(tp, 1, ins[1], mode.raw,
+                                                                                grad_ch=(0, ins[1].shape[1])))],
                      [seg, mid])[0]
 
 

@@ -6,7 +6,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import fast as _fast
-from .blocks import Attention, BaseNetwork, SPADEResnetBlock, conv_apply, equal_lr, nonspade_norm, norm_act
+from .blocks import (Attention, BaseNetwork, SPADEResnetBlock, conv_apply, equal_lr, nonspade_norm, norm_act,
+                     strict_convs)
 
 
 class SPADEGenerator(BaseNetwork):
@@ -41,6 +42,10 @@ class SPADEGenerator(BaseNetwork):
         seg = input if warp_out is None else warp_out
         if _fast.generator_supported(self, seg):  # 16-bit NHWC pipeline, every conv / norm on sm_100a kernels
             return _fast.generator_forward(self, seg)
+        with strict_convs(seg.is_cuda and _fast.conv_precision(self.opt) == "split"):
+            return self._forward_modules(seg)
+
+    def _forward_modules(self, seg):
         x = conv_apply(self.fc, F.interpolate(seg, size=(self.sh, self.sw)))
         x = self.head_0(x, seg)
         x = self.G_middle_0(self.up(x), seg)
@@ -97,7 +102,11 @@ class AdaptiveFeatureGenerator(BaseNetwork):
 
     def forward(self, input, seg):
         if seg is input and _fast.adaptor_supported(self, input):
-            return _fast.adaptor_forward(self, input, precise=getattr(self.opt, "conv_precision", "split") == "split")
+            return _fast.adaptor_forward(self, input, precise=_fast.conv_precision(self.opt) != "fast")
+        with strict_convs(input.is_cuda and _fast.conv_precision(self.opt) != "fast"):
+            return self._forward_modules(input, seg)
+
+    def _forward_modules(self, input, seg):
         # layer_{k+1}(actvn(layer_k(.))): the LeakyReLU(0.2) is fused into the norm of the layer that feeds it
         x = input
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
@@ -138,27 +147,32 @@ class DomainClassifier(BaseNetwork):
 
 
 class EMA:
-    """Exponential moving average of trainable parameters (generator.py:259-287)."""
+    """Exponential moving average of trainable parameters (generator.py:259-287).  Every update is IN PLACE on
+    storage allocated once: the average can be captured in the iteration's CUDA graph, and assign / resume swap values
+    (not storage), so parameters keep the addresses the graph and the fused optimiser hold."""
 
     def __init__(self, mu):
         self.mu = mu
         self.shadow, self.original = {}, {}
 
     def register(self, name, val):
-        self.shadow[name] = val.clone()
+        self.shadow[name] = val.detach().clone()
 
     def __call__(self, model):
         for name, p in model.named_parameters():
             if p.requires_grad:
-                self.shadow[name] = ((1.0 - self.mu) * p.data + self.mu * self.shadow[name]).clone()
+                self.shadow[name].mul_(self.mu).add_(p.data, alpha=1.0 - self.mu)
 
     def assign(self, model):
         for name, p in model.named_parameters():
             if p.requires_grad:
-                self.original[name] = p.data.clone()
-                p.data = self.shadow[name]
+                if name in self.original:
+                    self.original[name].copy_(p.data)
+                else:
+                    self.original[name] = p.data.clone()
+                p.data.copy_(self.shadow[name])
 
     def resume(self, model):
         for name, p in model.named_parameters():
             if p.requires_grad:
-                p.data = self.original[name]
+                p.data.copy_(self.original[name])

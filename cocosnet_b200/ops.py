@@ -221,16 +221,45 @@ def inst_act(x, slope=1.0, eps=1e-5):
     return _InstAct.apply(x, float(slope), float(eps))
 
 
-def normalize_pack(x, match_kernel, eps):
+def normalize_pack(x, match_kernel, eps, stats=False):
     """x [B,C,h,w] fp32 CUDA -> fp16 [B, h*w, C*mk*mk]: unfold + centre over K (--PONO_C) + L2-normalise + pack,
-    fused (no autograd: used on the inference / no-grad path)."""
+    fused.  stats=True also returns the per-position (mean, 1/(norm+eps)) the backward needs."""
     x = x.contiguous()
     _req(x, torch.float32, "x")
     b, c, h, w = x.shape
     out = torch.empty((b, h * w, c * match_kernel * match_kernel), dtype=torch.float16, device=x.device)
     ws = torch.empty((b, h * w, c), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().cocos_normalize_pack(x.data_ptr(), ws.data_ptr(), out.data_ptr(), b, c, h, w, match_kernel,
-                                               float(eps), _stream()), "cocos_normalize_pack", kernels=2)
+    mean = inv = None
+    if stats:
+        mean = torch.empty((b, h * w), dtype=torch.float32, device=x.device)
+        inv = torch.empty_like(mean)
+    _lib.check(_lib.lib().cocos_normalize_pack(x.data_ptr(), ws.data_ptr(), out.data_ptr(),
+                                               mean.data_ptr() if stats else None, inv.data_ptr() if stats else None,
+                                               b, c, h, w, match_kernel, float(eps), _stream()),
+               "cocos_normalize_pack", kernels=2)
+    return (out, mean, inv) if stats else out
+
+
+def normalize_pack_bwd(g, x, mean, inv, match_kernel):
+    """g = dL/d(operand) fp32 [B, K, N] (k = tap*C + c) -> dL/dx fp32 [B,C,h,w]."""
+    x = x.contiguous()
+    g = g.contiguous()
+    b, c, h, w = x.shape
+    assert g.shape == (b, c * match_kernel * match_kernel, h * w) and g.dtype == torch.float32
+    dx = torch.empty_like(x)
+    ws = torch.empty((2, b, h * w), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().cocos_normalize_pack_bwd(g.data_ptr(), x.data_ptr(), mean.data_ptr(), inv.data_ptr(),
+                                                   ws[0].data_ptr(), ws[1].data_ptr(), dx.data_ptr(), b, c, h, w,
+                                                   match_kernel, _stream()), "cocos_normalize_pack_bwd", kernels=2)
+    return dx
+
+
+def transpose_rows_bf16(x16):
+    """fp16 [B, N, K] -> bf16 [B, K, N]."""
+    b, n, k = x16.shape
+    out = torch.empty((b, k, n), dtype=torch.bfloat16, device=x16.device)
+    _lib.check(_lib.lib().cocos_transpose_f16_bf16(x16.data_ptr(), out.data_ptr(), b, n, k, _stream()),
+               "cocos_transpose_f16_bf16")
     return out
 
 

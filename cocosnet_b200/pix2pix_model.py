@@ -144,9 +144,12 @@ class Pix2PixModel(torch.nn.Module):
             input_semantics = zeros().scatter_(1, data["label"], 1.0)
             ref_semantics = zeros().scatter_(1, data["label_ref"], 1.0)
         if mode == "celebahq":
-            assert input_semantics[:, -3:-2].sum().item() == 0
+            # pix2pix_model.py:186-190 asserts that the glasses slot is empty; a host read cannot be captured into a
+            # CUDA graph, so the check only runs outside a capture (the eager warm-up iterations see the same data)
+            if not (input_semantics.is_cuda and torch.cuda.is_current_stream_capturing()):
+                assert input_semantics[:, -3:-2].sum().item() == 0
+                assert ref_semantics[:, -3:-2].sum().item() == 0
             input_semantics[:, -3:-2] = glasses
-            assert ref_semantics[:, -3:-2].sum().item() == 0
             ref_semantics[:, -3:-2] = glasses_ref
         if getattr(self.opt, "channels_last", False) and self.use_gpu():
             cl = torch.channels_last

@@ -52,6 +52,16 @@ def allreduce_grads(params, world=None):
     if world == 1:
         return 0
     grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    if dist.get_backend() == "nccl":
+        # ONE grouped NCCL launch over the gradient tensors themselves (ncclGroupStart / End around per-tensor
+        # all-reduces, averaged in the collective): no flatten, no copy-back, no separate division -- and a fixed
+        # sequence of device work, so it is captured into the iteration's CUDA graph like any other kernel.
+        with dist._coalescing_manager(device=grads[0].device, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        return 1
     buckets, cur, size = [], [], 0
     for g in grads:
         cur.append(g)
@@ -105,12 +115,14 @@ class Pix2PixTrainer:
                 ckpt = torch.load(os.path.join(opt.checkpoints_dir, opt.name, "optimizer.pth"), map_location="cpu")
                 self.optimizer_G.load_state_dict(ckpt["G"])
                 self.optimizer_D.load_state_dict(ckpt["D"])
+                self.old_lr = ckpt.get("lr", self.old_lr)  # resume mid-schedule (pix2pix_trainer.py:38-43)
             self._g_params = [p for k in ("netG", "netCorr") for p in net[k].parameters()]
             self._d_params = [p for p in net["netD"].parameters()]
         self.g_losses, self.d_losses, self.out = {}, {}, {}
         self._graph, self._static_in, self._eager_steps, self._side = None, None, 0, None
         self.graph_native_launches = 0
         self.graph_error = None
+        self._graph_key_captured = None
         self.pre_sharded = bool(getattr(opt, "pre_sharded", False))
         if opt.isTrain and "COCOS_NATIVE_DGRAD" not in os.environ:
             # K2 backward-data lowers the GPU-busy time but adds launches: it pays off once the iteration is replayed
@@ -122,7 +134,8 @@ class Pix2PixTrainer:
     GRAPH_WARMUP = 3  # eager iterations before the capture (cuDNN autotuning, lazy state, allocator warm-up)
 
     def graph_capable(self):
-        return (self.opt.isTrain and len(self.opt.gpu_ids) > 0 and _world() == 1
+        # with more than one rank the gradient all-reduce is captured with the iteration (NCCL only)
+        return (self.opt.isTrain and len(self.opt.gpu_ids) > 0 and (_world() == 1 or dist.get_backend() == "nccl")
                 and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
@@ -141,6 +154,9 @@ class Pix2PixTrainer:
         shapes are baked into the graph (update_learning_rate drops it; it is re-captured on the next call)."""
         if not self.graph_capable():
             return self._eager_step(data, alpha)
+        key = self._graph_key(alpha)
+        if self._graph is not None and key != self._graph_key_captured:
+            self._graph = None  # a value the step reads from Python changed: re-capture with it
         if self._graph is None:
             for pg in self.optimizer_G.param_groups + self.optimizer_D.param_groups:
                 pg["capturable"] = True  # before the first step: Adam's step counters live on the device
@@ -164,6 +180,16 @@ class Pix2PixTrainer:
         self._load_static(data)
         self._graph.replay()
 
+    def _graph_key(self, alpha):
+        """Everything the iteration reads from Python (and therefore bakes into a captured graph): alpha -- only the
+        gradient-reversal layer of the domain classifier reads it (correspondence.py:296-300, --weight_domainC > 0), it
+        changes every iteration there, so those configs are better left eager -- and the epoch-dependent branch of
+        NoVGGCorrespondence.forward (--noise_for_mask after --mask_epoch, correspondence.py:254-258); the learning
+        rate is handled by update_learning_rate."""
+        opt = self.opt
+        return (float(alpha) if opt.weight_domainC > 0 else None, bool(getattr(opt, "noise_for_mask", False)
+                                   and getattr(opt, "epoch", 0) > getattr(opt, "mask_epoch", 0)))
+
     def _capture(self, data, alpha):
         from . import _lib
         self._static_in = {k: torch.empty_like(v, device="cuda") for k, v in data.items() if torch.is_tensor(v)}
@@ -181,20 +207,33 @@ class Pix2PixTrainer:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         l0 = _lib.LAUNCHES
+        err = None
         try:
-            with torch.cuda.graph(graph):
+            # thread_local: NCCL's watchdog thread may query events while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if _world() > 1 else "global"):
                 self._eager_step(static, alpha)
         except Exception as e:  # noqa: BLE001 -- an op that cannot be captured: report it and keep training eagerly
-            self.graph_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+            err = "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+        if _world() > 1:  # all ranks replay or none does
+            flag = torch.tensor([0.0 if err is None else 1.0], device="cuda")
+            dist.all_reduce(flag)
+            if float(flag.item()) > 0 and err is None:
+                err = "capture failed on another rank"
+        if err is not None:
+            self.graph_error = err
             print("cocosnet_b200: CUDA-graph capture of the train step failed (%s); running eagerly" % self.graph_error)
             if os.environ.get("COCOS_GRAPH_TRACE", "0") == "1":
                 import traceback
                 traceback.print_exc()
             torch.cuda.synchronize()
             self._static_in = None
+            if "COCOS_NATIVE_DGRAD" not in os.environ:
+                from . import ops
+                ops.NATIVE_DGRAD = False  # the eager setting (see __init__)
             return
         self.graph_native_launches = _lib.LAUNCHES - l0
         self._graph = graph
+        self._graph_key_captured = self._graph_key(alpha)
 
     def _shard(self, data):
         """This rank's slice of a global batch; `pre_sharded` = the caller already hands over rank-local batches

@@ -86,3 +86,53 @@ def print_current_errors(opt, epoch, i, errors, t):  # util/util.py:320-331
             f.write("%s\n" % msg)
     except OSError as err:
         print(err)
+
+
+class IterationCounter:
+    """Epoch / iteration bookkeeping with resume (util/iter_counter.py:12-74): `<checkpoints>/<name>/iter.txt` holds
+    "epoch,iter_in_epoch"; --continue_train restarts from it, so the linear lr decay, `alpha` and the mask_epoch switch
+    pick up mid-schedule instead of at epoch 1."""
+
+    def __init__(self, opt, dataset_size):
+        import numpy as np
+        self.opt, self.dataset_size = opt, dataset_size
+        self.first_epoch, self.epoch_iter = 1, 0
+        self.total_epochs = opt.niter + opt.niter_decay
+        self.iter_record_path = os.path.join(opt.checkpoints_dir, opt.name, "iter.txt")
+        if opt.isTrain and opt.continue_train:
+            try:
+                self.first_epoch, self.epoch_iter = (int(v) for v in np.loadtxt(self.iter_record_path, delimiter=",",
+                                                                                 dtype=int))
+                print("Resuming from epoch %d at iteration %d" % (self.first_epoch, self.epoch_iter))
+            except (OSError, ValueError):
+                print("Could not load iteration record at %s. Starting from beginning." % self.iter_record_path)
+        self.total_steps_so_far = (self.first_epoch - 1) * dataset_size + self.epoch_iter
+        self.current_epoch = self.first_epoch
+
+    def training_epochs(self):
+        return range(self.first_epoch, self.total_epochs + 1)
+
+    def record_epoch_start(self, epoch):
+        self.epoch_iter, self.current_epoch = 0, epoch
+
+    def record_one_iteration(self):
+        self.total_steps_so_far += self.opt.batchSize
+        self.epoch_iter += self.opt.batchSize
+
+    def _write(self, epoch, it):
+        os.makedirs(os.path.dirname(self.iter_record_path), exist_ok=True)
+        with open(self.iter_record_path, "w") as f:
+            f.write("%d\n%d\n" % (epoch, it))  # np.savetxt's layout: one value per line
+
+    def record_epoch_end(self):
+        if self.current_epoch % self.opt.save_epoch_freq == 0:
+            self._write(self.current_epoch + 1, 0)
+
+    def record_current_iter(self):
+        self._write(self.current_epoch, self.epoch_iter)
+
+    def needs_saving(self):
+        return (self.total_steps_so_far % self.opt.save_latest_freq) < self.opt.batchSize
+
+    def needs_printing(self):
+        return (self.total_steps_so_far % self.opt.print_freq) < self.opt.batchSize

@@ -140,9 +140,19 @@ int cocos_cast_taps(const float* src, void* dst, long long rows, int Hin, int Wi
 /* Fused operand prologue for `--PONO_C` (correspondence.py:273-281 / 283-289): x fp32 [B,C,h,w] (output of the theta
  * or phi 1x1 conv) -> unfold(match_kernel, zero pad) -> minus the mean over K = C*mk*mk -> / (L2 norm over K + eps)
  * -> fp16 [B, h*w, K], K laid out tap-major (k = tap*C + c; use the same call for both operands).  xt_workspace:
- * fp32 scratch of B*C*h*w elements.  match_kernel in {1, 3}; C % 4 == 0; K % 64 == 0. */
-int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, int B, int C, int h, int w, int match_kernel,
-                         float eps, void* stream);
+ * fp32 scratch of B*C*h*w elements.  match_kernel in {1, 3}; C % 4 == 0; K % 64 == 0.  mean_out / inv_out (both or
+ * neither; [B, h*w] fp32): the per-position mean and 1 / (norm + eps), kept for the backward. */
+int cocos_normalize_pack(const float* x, float* xt_workspace, void* out, float* mean_out, float* inv_out, int B, int C,
+                         int h, int w, int match_kernel, float eps, void* stream);
+/* Backward of cocos_normalize_pack (autograd through correspondence.py:273-289: normalise, centre, unfold):
+ * g = dL/d(operand) fp32 [B, K, h*w] (k = tap*C + c, the layout cocos_gemm_f16 emits for K_cm . dS) -> dx fp32
+ * [B,C,h,w]; a_ws / s_ws: fp32 scratch [B, h*w] each.  The unfolded [B, K, N] tensors never exist: the fold is a
+ * 9-term gather per pixel. */
+int cocos_normalize_pack_bwd(const float* g, const float* x, const float* mean, const float* inv, float* a_ws,
+                             float* s_ws, float* dx, int B, int C, int h, int w, int match_kernel, void* stream);
+/* fp16 [B, N, K] (a packed operand) -> bf16 [B, K, N]: the channel-major A operands of the dQ / dK GEMMs of the
+ * correspondence backward without keeping the fp32 [B, K, N] tensors of the forward. */
+int cocos_transpose_f16_bf16(const void* src, void* dst, int B, int N, int K, void* stream);
 
 /* Fused InstanceNorm2d(affine=False, eps) + LeakyReLU(slope) over `planes` = B*C contiguous planes of HW fp32
  * elements (NCHW): the norm/activation pairs of the domain adaptor (generator.py:104-113,141-145) and of the

@@ -269,3 +269,30 @@ def spade_modulate(x, gamma, beta, leaky=None):
     if leaky is not None:
         out = np.where(out >= 0, out, out * leaky)
     return out
+
+
+def operand_prologue_backward(x, g, match_kernel=3):
+    """Gradient of the --PONO_C operand prologue (unfold -> centre over K -> L2-normalise, correspondence.py:273-289)
+    w.r.t. the conv output x [B,C,h,w], given g = dL/d(operand) [B,K,N] in the product's TAP-MAJOR K order
+    (k = tap*C + c).  Restates the two passes of cocos_normalize_pack_bwd (per-position a = <fhat, g>, s = sum g;
+    then a 9-term gather per pixel) so that the formula -- not just the kernel -- is pinned to autograd of the
+    reference expression (tests/test_oracle_golden.py::test_operand_prologue_backward_matches_autograd)."""
+    x = np.asarray(x, np.float64)
+    g = np.asarray(g, np.float64)
+    B, C, h, w = x.shape
+    mk, half = match_kernel, match_kernel // 2
+    taps = [(r - half, s - half) for r in range(mk) for s in range(mk)]
+    K = C * len(taps)
+    xp = np.pad(x, ((0, 0), (0, 0), (half, half), (half, half)))
+    f = np.stack([xp[:, :, half + di:half + di + h, half + dj:half + dj + w] for di, dj in taps], 1)  # [B,T,C,h,w]
+    f = f.reshape(B, K, h * w)
+    mean = f.mean(1, keepdims=True)
+    inv = 1.0 / (np.sqrt(((f - mean) ** 2).sum(1, keepdims=True)) + EPS)
+    fhat = (f - mean) * inv
+    a = (fhat * g).sum(1, keepdims=True)
+    s = g.sum(1, keepdims=True)
+    df = ((g - fhat * a - s / K) * inv).reshape(B, len(taps), C, h, w)
+    dx = np.zeros((B, C, h + 2 * half, w + 2 * half))
+    for t, (di, dj) in enumerate(taps):  # the fold: position n contributed x[., n + offset(t)]
+        dx[:, :, half + di:half + di + h, half + dj:half + dj + w] += df[:, t]
+    return dx[:, :, half:half + h, half:half + w]

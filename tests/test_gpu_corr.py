@@ -326,6 +326,63 @@ def test_normalize_pack_fused_vs_oracle(mk):
     assert np.abs(out - want_tm).max() < 1e-3 * np.abs(want_tm).max() + 1e-4  # fp16 rounding of unit vectors
 
 
+@pytest.mark.parametrize("mk,C,h,w", [(3, 64, 12, 20), (1, 64, 12, 20), (3, 256, 64, 64)])
+def test_normalize_pack_backward_vs_oracle(mk, C, h, w):
+    """cocos_normalize_pack (statistics saved) + cocos_normalize_pack_bwd vs the oracle's restatement of the two-pass
+    formula (itself pinned to autograd of the reference expressions on CPU)."""
+    from cocosnet_b200 import ops
+    from oracle import corr_oracle as oc
+    rng = np.random.default_rng(10 * mk + C)
+    B = 2
+    x = rng.standard_normal((B, C, h, w)).astype(np.float32) + 0.3
+    g = rng.standard_normal((B, C * mk * mk, h * w)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    q16, mean, inv = ops.normalize_pack(xt, mk, 2.220446049250313e-16, stats=True)
+    assert torch.equal(q16, ops.normalize_pack(xt, mk, 2.220446049250313e-16))
+    dx = ops.normalize_pack_bwd(torch.from_numpy(g).cuda(), xt, mean, inv, mk).cpu().numpy()
+    want = oc.operand_prologue_backward(x, g, mk)
+    assert _rel(dx, want) < 2e-5
+    cm = ops.transpose_rows_bf16(q16)
+    assert torch.equal(cm.float(), q16.float().bfloat16().float().transpose(1, 2))
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(warp_mask_losstype="direct"), dict(warp_cycle=True, two_cycle=True),
+                                   dict(warp_mask_losstype="cycle")])
+def test_train_path_fused_prologue_matches_unfused_tail(flags, monkeypatch):
+    """correspondence_tail with autograd: the packed-operand path (fused prologue kernels forward AND backward, operand
+    gradients accumulated over every attend that shares them) against the torch-op prologue feeding the same K1."""
+    from cocosnet_b200 import corr
+    g = torch.Generator().manual_seed(3)
+    B, C, h, w = 2, 64, 16, 16
+    theta0 = torch.randn(B, C, h, w, generator=g).cuda()
+    phi0 = (0.7 * theta0.cpu() + 0.7 * torch.randn(B, C, h, w, generator=g)).cuda()
+    ref_img = torch.rand(B, 3, 64, 64, generator=g).cuda() * 2 - 1
+    real_img = torch.rand(B, 3, 64, 64, generator=g).cuda() * 2 - 1
+    seg = torch.zeros(B, 10, 64, 64).scatter_(1, torch.randint(0, 10, (B, 1, 64, 64), generator=g), 1.0).cuda()
+    ref_seg = torch.zeros(B, 10, 64, 64).scatter_(1, torch.randint(0, 10, (B, 1, 64, 64), generator=g), 1.0).cuda()
+    wts = [torch.randn(B, 3, 16, 16, generator=g).cuda() for _ in range(4)]
+
+    def run(fused):
+        monkeypatch.setattr(corr, "FUSED_PROLOGUE", fused)
+        theta, phi = theta0.clone().requires_grad_(True), phi0.clone().requires_grad_(True)
+        y, ex = corr.correspondence_tail(theta, phi, ref_img, match_kernel=3, pono_c=True, temperature=0.05,
+                                         ref_seg_map=ref_seg, seg_map=seg, real_img=real_img, **flags)
+        loss = (y * wts[0]).sum()
+        for i, k in enumerate(sorted(ex)):
+            loss = loss + (ex[k][:, :3] * wts[1 + i % 3]).sum()
+        loss.backward()
+        return y.detach(), {k: v.detach() for k, v in ex.items()}, theta.grad, phi.grad
+
+    yf, exf, gtf, gpf = run(True)
+    yu, exu, gtu, gpu_ = run(False)
+    assert _rel(yf.cpu().numpy(), yu.cpu().numpy()) < 2e-3
+    for k in exu:
+        assert _rel(exf[k].cpu().numpy(), exu[k].cpu().numpy()) < 2e-3, k
+    # gradients: bf16 dS on both sides, different K order / operand rounding of the GEMM A operands
+    assert _rel(gtf.cpu().numpy(), gtu.cpu().numpy()) < 2e-2
+    assert _rel(gpf.cpu().numpy(), gpu_.cpu().numpy()) < 2e-2
+
+
 def test_tail_inference_path_uses_fused_prologue_and_matches_golden():
     from cocosnet_b200 import corr
     from tests.golden import cases

@@ -43,34 +43,19 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
 
-@pytest.mark.timeout(900)
-@pytest.mark.parametrize("native_conv", [False, True])
-@pytest.mark.parametrize("config", list(MODEL_CONFIGS))
-def test_train_step_matches_reference_golden(config, native_conv):
-    """native_conv=False: every convolution in fp32 (cuDNN, TF32 off) -> the 1e-3 bar on the outputs.
-    native_conv=True: conv forwards on the tcgen05 kernel with fp16 operands (TF32-class rounding, what stock
-    PyTorch does by default on this GPU) -> 5e-3 on the generator output, same bar on the correspondence."""
-    from cocosnet_b200 import data as cdata, ops
-    gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
-    old = torch.backends.cudnn.allow_tf32
-    old_native, old_dgrad = ops.NATIVE_CONV, ops.NATIVE_DGRAD
-    torch.backends.cudnn.allow_tf32 = False  # strict numerics for the parity check
-    ops.NATIVE_CONV = ops.NATIVE_DGRAD = native_conv  # native: forward, backward-data and backward-weights on K2
-    tol = 5.0 if native_conv else 1.0
-    try:
-        opt, model = _build(gpu=True, config=config)
-        batch = cdata.synthetic_batch(opt, 1)
-        g_losses, out = model(batch, mode="generator")
-        sum(g_losses.values()).mean().backward()
-        d_losses = model(batch, mode="discriminator", GforD={"fake_image": out["fake_image"]})
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
-        ops.NATIVE_CONV, ops.NATIVE_DGRAD = old_native, old_dgrad
-    # outputs: north-star tolerance 1e-3 relative
-    # (TF32-class conv rounding upstream of the correlation is amplified by 1/temperature = 100: measured
-    #  3e-3..6e-3 on warp_out for cuDNN-TF32 and for the native kernels alike, profiles/r01_precision_modes.txt)
-    assert _rel(out["warp_out"].detach().cpu().numpy()[:, :, ::4, ::4], gold["warp_out_sub"]) < (1e-2 if native_conv else 1e-3)
-    assert _rel(out["fake_image"].detach().cpu().numpy()[:, :, ::4, ::4], gold["fake_image_sub"]) < 1e-3 * tol
+def _train_step(config, precision):
+    from cocosnet_b200 import data as cdata
+    opt, model = _build(gpu=True, config=config)
+    if precision is not None:
+        opt.conv_precision = precision
+    batch = cdata.synthetic_batch(opt, 1)
+    g_losses, out = model(batch, mode="generator")
+    sum(g_losses.values()).mean().backward()
+    d_losses = model(batch, mode="discriminator", GforD={"fake_image": out["fake_image"]})
+    return model, g_losses, d_losses, out
+
+
+def _check_losses_and_grads(model, gold, g_losses, d_losses, out, tol):
     if "warp_mask_chsum" in gold.files:
         assert np.abs(out["warp_mask"].detach().cpu().numpy().sum(1) - gold["warp_mask_chsum"]).max() < 2e-3
     if "warp_cycle" in gold.files:
@@ -81,13 +66,46 @@ def test_train_step_matches_reference_golden(config, native_conv):
     for k, v in d_losses.items():
         want = float(gold["d_" + k][0])
         assert abs(float(v.mean()) - want) <= 2e-3 * tol * abs(want), k
-    # gradients through the fused backward (fp16 dS): looser
+    # gradients run on bf16 operands (fp32 range for GAN gradients; 8 mantissa bits): looser
     for key in gold.files:
         if key.startswith("gradnorm_"):
             _, netk, pname = key.split("_", 2)
             p = dict(model.net[netk].named_parameters())[pname]
-            assert abs(float(p.grad.norm()) - float(gold[key][0])) <= 2e-2 * float(gold[key][0]), \
+            assert abs(float(p.grad.norm()) - float(gold[key][0])) <= 3e-2 * float(gold[key][0]), \
                 (key, float(p.grad.norm()), float(gold[key][0]))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("config", list(MODEL_CONFIGS))
+def test_train_step_matches_reference_golden(config):
+    """The DEFAULT path -- exactly what bench.py times (--conv_precision split, --corr_precision auto, global cuDNN /
+    TF32 flags untouched) -- against the goldens minted from the unmodified reference: the north-star bar, 1e-3
+    relative on warp_out AND fake_image, for BASELINE configs[1..3] at batch 1."""
+    gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
+    model, g_losses, d_losses, out = _train_step(config, None)
+    assert model.opt.conv_precision == "split" and model.opt.corr_precision == "auto"
+    warp = _rel(out["warp_out"].detach().cpu().numpy()[:, :, ::4, ::4], gold["warp_out_sub"])
+    fake = _rel(out["fake_image"].detach().cpu().numpy()[:, :, ::4, ::4], gold["fake_image_sub"])
+    print(config, "warp_out %.2e fake_image %.2e" % (warp, fake))
+    assert warp < 1e-3, warp
+    assert fake < 1e-3, fake
+    _check_losses_and_grads(model, gold, g_losses, d_losses, out, 1.0)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("precision", ["mixed", "fast"])
+def test_train_step_reduced_precision_modes(precision):
+    """The opt-in faster modes (NOT the default, NOT what bench.py times): 'mixed' keeps the correspondence path on
+    split operands (warp_out still at the bar) and runs the generator on single fp16 terms (TF32-class, measured
+    1.1e-3 on fake_image); 'fast' uses single terms everywhere (1/temperature amplifies them to ~5e-3 on warp_out)."""
+    gold = np.load(os.path.join(GOLD, "model_ade20k_train.npz"))
+    model, g_losses, d_losses, out = _train_step("ade20k_train", precision)
+    warp = _rel(out["warp_out"].detach().cpu().numpy()[:, :, ::4, ::4], gold["warp_out_sub"])
+    fake = _rel(out["fake_image"].detach().cpu().numpy()[:, :, ::4, ::4], gold["fake_image_sub"])
+    print(precision, "warp_out %.2e fake_image %.2e" % (warp, fake))
+    assert warp < (1e-3 if precision == "mixed" else 1e-2), warp
+    assert fake < 5e-3, fake
+    _check_losses_and_grads(model, gold, g_losses, d_losses, out, 5.0)
 
 
 def test_inference_mode_runs_and_is_deterministic():
@@ -110,16 +128,21 @@ def test_inference_mode_runs_and_is_deterministic():
 
 
 @pytest.mark.timeout(900)
-def test_graphed_train_step_tracks_eager(monkeypatch):
-    """trainer.run_step: eager for GRAPH_WARMUP calls, then ONE CUDA graph per iteration.  Same seed, same batches:
-    the losses after 6 iterations agree with a trainer that never captures (split-K atomics and cuDNN algorithm
-    choices make the two runs differ in the last bits, hence a tolerance, not equality)."""
+def test_graph_replay_equals_eager_step_from_the_same_state():
+    """trainer.run_step: eager for GRAPH_WARMUP calls, then ONE CUDA graph per iteration.  Equivalence, not just
+    "it trains": the state (weights, spectral-norm vectors, Adam moments and step counters) is snapshotted right before
+    the first replay, the replayed iteration and an EAGER iteration of a second trainer loaded with that snapshot run
+    on the same batch, and losses and updated weights must agree to the run-to-run noise of split-K atomics."""
+    import copy
     from cocosnet_b200 import data as cdata
     from cocosnet_b200.options import TrainOptions
     from cocosnet_b200.trainer import Pix2PixTrainer
     from oracle import torch_port
 
-    def run(use_graph):
+    if os.environ.get("COCOS_CUDA_GRAPH", "1") != "1":
+        pytest.skip("CUDA-graph step disabled by COCOS_CUDA_GRAPH=0")
+
+    def make(use_graph):
         opt = TrainOptions().parse(ADE_TRAIN[:-1] + ["2", "--gpu_ids", "0"], save=False, verbose=False)
         opt.verbose_networks = False
         opt.allow_random_vgg = True
@@ -128,57 +151,64 @@ def test_graphed_train_step_tracks_eager(monkeypatch):
         trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
         if not use_graph:
             trainer.graph_error = "disabled for the comparison"
-        hist = []
-        for it in range(6):
-            batch = cdata.synthetic_batch(opt, 2, seed=100 + it)
-            trainer.run_step(batch)
-            hist.append({k: float(v.mean()) for k, v in trainer.get_latest_losses().items()})
-        return trainer, hist
+        return opt, trainer
 
-    if os.environ.get("COCOS_CUDA_GRAPH", "1") != "1":
-        pytest.skip("CUDA-graph step disabled by COCOS_CUDA_GRAPH=0")
-    tg, hg = run(True)
+    opt, tg = make(True)
+    for it in range(tg.GRAPH_WARMUP):
+        tg.run_step(cdata.synthetic_batch(opt, 2, seed=100 + it))
+    assert tg._graph is None
+    torch.cuda.synchronize()
+    snap = {"model": copy.deepcopy(tg.pix2pix_model.state_dict()), "G": copy.deepcopy(tg.optimizer_G.state_dict()),
+            "D": copy.deepcopy(tg.optimizer_D.state_dict())}
+    batch = cdata.synthetic_batch(opt, 2, seed=777)
+    tg.run_step(batch)  # capture + first replay
     assert tg._graph is not None, tg.graph_error
     assert tg.graph_native_launches > 100
-    te, he = run(False)
+    lg = {k: float(v.mean()) for k, v in tg.get_latest_losses().items()}
+
+    _, te = make(False)
+    te.pix2pix_model.load_state_dict(snap["model"])
+    te.optimizer_G.load_state_dict(snap["G"])
+    te.optimizer_D.load_state_dict(snap["D"])
+    te.run_step(batch)
     assert te._graph is None
-    print("graphed:", hg)
-    print("eager:  ", he)
-    # iteration 3 is the first replay.  Everything but the mask loss agrees to 3e-2 there (measured: <= 6e-3; the
-    # mask term, a log of tiny probabilities weighted by 100, already differs by 2e-4 between two EAGER runs at
-    # iteration 1 because of split-K / atomics ordering, and by 15 % at iteration 3); two replays later the slow
-    # reconstruction losses still agree while the adversarial ones have diverged chaotically (batch 2, random data).
-    for k in he[3]:
-        tol = 0.5 if k == "mask" else 3e-2
-        assert abs(hg[3][k] - he[3][k]) <= tol * max(abs(he[3][k]), 1.0), (3, k, hg[3][k], he[3][k])
-    for k in ("perc", "contextual", "fm"):
-        assert abs(hg[5][k] - he[5][k]) <= 3e-2 * abs(he[5][k]), (5, k, hg[5][k], he[5][k])
-    # the graph really trains: losses move between replays and the weights differ from the start
-    assert any(abs(hg[-1][k] - hg[-2][k]) > 0 for k in hg[-1])
+    le = {k: float(v.mean()) for k, v in te.get_latest_losses().items()}
+    print("graphed:", lg)
+    print("eager:  ", le)
+    for k in le:
+        assert abs(lg[k] - le[k]) <= 2e-3 * max(abs(le[k]), 1.0), (k, lg[k], le[k])
+    # the weights after the update: the Adam step is lr-sized for every element, so compare the UPDATES
+    pg, pe = dict(tg.pix2pix_model.named_parameters()), dict(te.pix2pix_model.named_parameters())
+    worst = 0.0
+    for name in ("net.netG.fc.weight", "net.netG.conv_img.weight", "net.netCorr.theta.weight",
+                 "net.netD.discriminator_0.model0.0.weight"):
+        before = snap["model"][name].float()
+        ug, ue = pg[name].detach().float() - before, pe[name].detach().float() - before
+        assert float(ue.norm()) > 0, name
+        worst = max(worst, float((ug - ue).norm() / ue.norm()))
+    print("relative difference of the parameter updates: %.2e" % worst)
+    assert worst < 5e-2, worst
+    # and the graph keeps training: a second replay moves the losses
+    tg.run_step(cdata.synthetic_batch(opt, 2, seed=778))
+    l2 = {k: float(v.mean()) for k, v in tg.get_latest_losses().items()}
+    assert any(abs(l2[k] - lg[k]) > 0 for k in l2)
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("native_conv", [False, True])
 @pytest.mark.parametrize("config", ["ade20k_infer_mk3", "ade20k_infer_mk1"])
-def test_inference_matches_reference_golden(config, native_conv):
-    """BASELINE configs[0]: `mode='inference'` on the GPU (fused normalise+pack prologue, K1, K2) against what the
-    unmodified reference produced on the CPU for the same seeded weights and batch.  Bounds as in the train-step
-    test: fp32 convs -> the fp16-operand correlation is the only rounding (measured <= 9e-4 at K = 256); K2 convs ->
-    TF32-class error amplified by 1/T = 100 on warp_out."""
-    from cocosnet_b200 import data as cdata, ops
+def test_inference_matches_reference_golden(config):
+    """BASELINE configs[0]: `mode='inference'` on the GPU in the DEFAULT mode (fused normalise+pack prologue at
+    K = 2304, 3-term split operands at K = 256, every convolution on the NHWC tape in split precision) against what the
+    unmodified reference produced on the CPU for the same seeded weights and batch: 1e-3 on both outputs."""
+    from cocosnet_b200 import data as cdata
     from tests.test_model_parity_cpu import build_inference_model
     gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
-    old_tf32, old_native = torch.backends.cudnn.allow_tf32, ops.NATIVE_CONV
-    torch.backends.cudnn.allow_tf32 = False
-    ops.NATIVE_CONV = native_conv
-    try:
-        opt, model = build_inference_model(config, gpu=True)
-        batch = cdata.synthetic_batch(opt, 1)
-        with torch.no_grad():
-            out = model(batch, mode="inference")
-    finally:
-        torch.backends.cudnn.allow_tf32, ops.NATIVE_CONV = old_tf32, old_native
+    opt, model = build_inference_model(config, gpu=True)
+    batch = cdata.synthetic_batch(opt, 1)
+    with torch.no_grad():
+        out = model(batch, mode="inference")
     warp = _rel(out["warp_out"].cpu().numpy()[:, :, ::4, ::4], gold["warp_out_sub"])
     fake = _rel(out["fake_image"].cpu().numpy()[:, :, ::4, ::4], gold["fake_image_sub"])
-    assert warp < (2e-2 if native_conv else 2e-3), warp
-    assert fake < (8e-3 if native_conv else 2e-3), fake
+    print(config, "warp_out %.2e fake_image %.2e" % (warp, fake))
+    assert warp < 1e-3, warp
+    assert fake < 1e-3, fake

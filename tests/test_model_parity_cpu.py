@@ -25,7 +25,7 @@ def test_option_defaults_match_reference_snapshot():
     for name, (argv, is_train) in snap["cases"].items():
         cls = TrainOptions if is_train else _TestOptions
         opt = cls().parse(argv + ["--gpu_ids", "-1"], save=False, verbose=False)
-        mine = {k: v for k, v in vars(opt).items() if k not in ("gpu_ids", "corr_precision", "channels_last")}
+        mine = {k: v for k, v in vars(opt).items() if k not in ("gpu_ids", "corr_precision", "conv_precision", "channels_last")}
         ref = {k: v for k, v in snap["values"][name].items() if k not in ("gpu_ids", "down")}
         for k, v in ref.items():
             mv = mine[k]

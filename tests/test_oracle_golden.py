@@ -71,3 +71,23 @@ def test_bilinear_and_unfold_match_torch():
     assert np.allclose(oc.fold(u, 8, 4, 4), x)
     assert np.allclose(oc.positional_norm(x), ((torch.tensor(x) - torch.tensor(x).mean(1, keepdim=True))
                        / torch.tensor(x).var(1, keepdim=True).add(1e-5).sqrt()).numpy(), atol=1e-12)
+
+
+@pytest.mark.parametrize("mk", [1, 3])
+def test_operand_prologue_backward_matches_autograd(mk):
+    """The two-pass backward formula of the fused operand prologue (cocos_normalize_pack_bwd) == autograd through the
+    reference's unfold / centre / normalise expressions (correspondence.py:273-289, --PONO_C)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    B, C, h, w = 2, 8, 6, 5
+    x = rng.standard_normal((B, C, h, w))
+    g_ref_order = rng.standard_normal((B, C * mk * mk, h * w))  # F.unfold order: k = c*mk*mk + tap
+    xt = torch.tensor(x, requires_grad=True)
+    f = F.unfold(xt, kernel_size=mk, padding=mk // 2) if mk > 1 else xt.reshape(B, C, -1)
+    f = f - f.mean(dim=1, keepdim=True)
+    f = f / (torch.norm(f, 2, 1, keepdim=True) + oc.EPS)
+    (f * torch.tensor(g_ref_order)).sum().backward()
+    g_tap_major = g_ref_order.reshape(B, C, mk * mk, h * w).transpose(0, 2, 1, 3).reshape(B, C * mk * mk, h * w)
+    got = oc.operand_prologue_backward(x, g_tap_major, mk)
+    assert np.allclose(got, xt.grad.numpy(), rtol=1e-9, atol=1e-12)
