@@ -20,13 +20,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLAGS = ["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C"]
+# BASELINE.json configs by index: flags, per-GPU batch (configs[k] batchSize / its GPU count = 8 everywhere)
+CONFIGS = {
+    1: ("ade20k 256x256 --use_attention --maskmix --PONO --PONO_C", FLAGS),
+    2: ("celebahq 256x256 --warp_bilinear --adaptor_kernel 4",
+        ["--dataset_mode", "celebahq", "--warp_bilinear", "--adaptor_kernel", "4"]),
+    3: ("deepfashion 256x256 --warp_patch --video_like", ["--dataset_mode", "deepfashion", "--warp_patch", "--video_like"]),
+    4: ("ade20k 256x256 full training config (README flags: + --warp_mask_losstype direct --weight_mask 100 "
+        "--vgg_normal_correct)", FLAGS + ["--warp_mask_losstype", "direct", "--weight_mask", "100.0", "--vgg_normal_correct"]),
+}
 PER_GPU_BATCH = 8
 METRIC = "images/sec ADE20k 256x256 train step"
+STEP_TFLOP_PER_IMAGE = 4.18  # algorithmic FLOPs of one G+D train step per image (configs[1])
 
 
-def make_opt(batch, gpu, device_index=0):
+def make_opt(batch, gpu, device_index=0, flags=None):
     from cocosnet_b200.options import TrainOptions
-    argv = FLAGS + ["--batchSize", str(batch), "--gpu_ids", str(device_index) if gpu else "-1", "--name", "bench"]
+    argv = (FLAGS if flags is None else flags) + ["--batchSize", str(batch), "--gpu_ids",
+                                                  str(device_index) if gpu else "-1", "--name", "bench"]
     opt = TrainOptions().parse(argv, save=False, verbose=False)
     opt.verbose_networks = False
     opt.allow_random_vgg = True  # models/vgg19_conv.pth is not redistributable: seeded random VGG
@@ -114,7 +125,7 @@ def k1_roofline(torch, batch=8, n=4096, kd=256, cv=3, iters=20):
         traffic = json.load(open(summ)).get("dram_bytes_per_launch")
     return {"bound": "tensor", "kernel": "corr_fwd4_kernel (fused correlation+softmax+warp)", "achieved": achieved,
             "peak": peak, "peak_source": src + " cuBLAS bf16 burst", "unit": "TFLOP/s", "frac": achieved / peak,
-            "frac_of_nominal_2250": achieved / 2250.0, "traffic": traffic,
+            "frac_of_nominal_2250": achieved / 2250.0, "traffic": traffic if kd == 256 else None,
             "shape": {"batch": batch, "HW": n, "C": kd, "Cv": cv}, "ms_per_launch": ms,
             "algorithmic_flops_per_launch": flops}
 
@@ -135,7 +146,7 @@ def cpu_step_images_per_sec(steps, warmup, budget_s=240.0):
     opt = make_opt(1, gpu=False)
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
-    trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+    trainer.pix2pix_model.vggnet_fix.load_state_dict(cdata.seeded_vgg_state_dict())
     batch = cdata.synthetic_batch(opt, 1)
     times = []
     with torch_port.cpu_reference_mode():
@@ -158,7 +169,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs index (1: the headline ade20k step; 2 celebahq, 3 deepfashion, 4 ade20k "
+                         "with the README's full flag set); 8 images per GPU in all of them")
+    ap.add_argument("--stock-torch", action="store_true",
+                    help="MEASUREMENT ONLY: every hand-written kernel off (reference expressions on cuDNN / cuBLAS)")
     args = ap.parse_args()
+    if args.stock_torch:
+        os.environ["COCOS_STOCK_TORCH"] = "1"
+        os.environ["COCOS_CUDA_GRAPH"] = "0"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,17 +207,23 @@ def main():
     from cocosnet_b200 import _lib
     from cocosnet_b200 import data as cdata
     from cocosnet_b200.trainer import Pix2PixTrainer
-    from oracle import torch_port
 
     assert torch.cuda.is_available(), "bench.py needs CUDA (no CPU fallback for the product path)"
     _lib.lib()
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the gradient all-reduce is captured into the iteration's CUDA graph: NCCL's watchdog must not poll events of
+        # a capturing stream (PyTorch's documented recipe for whole-network capture with NCCL)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    opt = make_opt(PER_GPU_BATCH, gpu=True, device_index=local_rank)
+    workload, flags = CONFIGS[args.config]
+    opt = make_opt(PER_GPU_BATCH, gpu=True, device_index=local_rank, flags=flags)
+    if args.stock_torch:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = \
+            os.environ.get("COCOS_STOCK_TF32", "1") == "1"
     torch.manual_seed(0)
     trainer = Pix2PixTrainer(opt)
-    trainer.pix2pix_model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+    trainer.pix2pix_model.vggnet_fix.load_state_dict(cdata.seeded_vgg_state_dict())
     # weak scaling: every rank owns a distinct batch of 8 (global batch = 8 * N); the trainer's
     # shard_batch() is bypassed by handing it the rank-local shard directly
     trainer.pre_sharded = True
@@ -258,30 +284,70 @@ def main():
     d2h = 4 * len(trainer.get_latest_losses())
     ms_e2e = timed(step_e2e, args.steps)
 
-    roof = cpu = None
+    if args.stock_torch:
+        if rank == 0:
+            print(json.dumps({"stock_torch": True, "tf32": bool(torch.backends.cudnn.allow_tf32),
+                              "value": PER_GPU_BATCH * world * args.steps / (ms / 1e3), "unit": "images/sec",
+                              "ms_per_step": ms / args.steps, "e2e": PER_GPU_BATCH * world * args.steps / (ms_e2e / 1e3),
+                              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    roof = roof_k2304 = cpu = gpu_base = None
     if rank == 0:
         roof = k1_roofline(torch)
+        roof_k2304 = k1_roofline(torch, kd=2304, iters=10)  # the K the train step itself runs (match_kernel 3)
     if world > 1:
         dist.barrier()
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        # stock PyTorch on this same GPU (cuDNN / cuBLAS, TF32 on -- PyTorch's default -- and off), eager, in fresh
+        # processes so that neither the allocator state nor the flags leak
+        gpu_base = {}
+        trainer.free_graph()
+        torch.cuda.empty_cache()
+        for name, tf32 in (("tf32", "1"), ("fp32", "0")):
+            env = dict(os.environ, COCOS_STOCK_TF32=tf32)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--stock-torch", "--config", str(args.config),
+                                      "--steps", "3", "--warmup", "3"], env=env, capture_output=True, text=True, timeout=600)
+                gpu_base[name] = json.loads(out.stdout.strip().splitlines()[-1])
+            except Exception as e:  # noqa: BLE001
+                gpu_base[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, timed_n, cores = cpu_step_images_per_sec(1, 1, budget_s=45.0)
+        ips, timed_n, cores = cpu_step_images_per_sec(5, 1, budget_s=120.0)
         cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
                "sample": "%d timed G+D train step(s) at batch 1 on host cores (CPU port of the reference step)" % timed_n}
     if rank == 0:
         gb = PER_GPU_BATCH * world
-        line = {"metric": METRIC, "value": gb * args.steps / (ms / 1e3), "unit": "images/sec", "n_gpus": world,
+        value = gb * args.steps / (ms / 1e3)
+        _, sustained, psrc = measured_peaks()
+        step_roof = None
+        if args.config in (1, 4):
+            ach = value / world * STEP_TFLOP_PER_IMAGE
+            step_roof = {"bound": "tensor", "achieved": ach, "peak": sustained, "peak_source": psrc + " cuBLAS bf16 sustained",
+                         "unit": "TFLOP/s", "frac": ach / sustained, "per": "GPU",
+                         "algorithmic_tflop_per_image": STEP_TFLOP_PER_IMAGE,
+                         "note": "algorithmic FLOPs (SURVEY 8d); the default precision mode spends 3 MMAs per tap on "
+                                 "the convolutions upstream of warp_out / fake_image (2-term split operands, 1e-3 parity)"}
+        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (forward) / bf16 (backward) operands on tcgen05 for correspondence, attention and stride-1 convs; tf32 for the remaining library convs; fp32 accumulate",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp16 2-term split operands (forward, fp32 accumulate on tcgen05) on every convolution upstream "
+                         "of warp_out / fake_image, single fp16 terms in the PatchGANs and VGG19, bf16 operands in the "
+                         "backward; fp16 operands in the fused correspondence kernel",
+                "precision_mode": {"conv_precision": opt.conv_precision, "corr_precision": opt.corr_precision,
+                                   "parity": "tests/test_gpu_model.py asserts 1e-3 on warp_out and fake_image in "
+                                             "exactly this mode"},
                 "data": "synthetic",
-                "config": {"workload": "ade20k 256x256 --use_attention --maskmix --PONO --PONO_C, full G+D train step "
-                                       "(fwd+bwd+Adam), match_kernel 3 (K=2304), BASELINE configs[1]",
+                "config": {"workload": workload + ", full G+D train step (fwd+bwd+Adam), BASELINE configs[%d]" % args.config,
                            "global_batch": gb, "per_gpu_batch": PER_GPU_BATCH, "parallelism": "dp%d" % world,
                            "cuda_graph": graphed if trainer.graph_error is None else "capture failed: " + trainer.graph_error,
                            "l2": "per-step activations (multi-GB) and inputs exceed the 126 MB L2; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": gb * args.steps / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "roofline": roof, "roofline_k2304": roof_k2304, "step_roofline": step_roof,
+                "gpu_baseline": gpu_base, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -137,9 +137,18 @@ class _AttendPacked(torch.autograd.Function):
         return zero(need_q), zero(need_k), dv, None, None, None
 
 
+def _attend_stock(q, k, v, scale):
+    """The reference's own three ops (correspondence.py:291,304-307,318) -- only under ops.STOCK_TORCH (bench.py's
+    stock-PyTorch GPU baseline)."""
+    f = torch.matmul(q.permute(0, 2, 1), k) * scale
+    return torch.matmul(torch.softmax(f, dim=-1), v.permute(0, 2, 1)).permute(0, 2, 1)
+
+
 def attend(q, k, v, scale, precision="fp16"):
     """q [B,Kd,Nq], k [B,Kd,Nk], v [B,Cv,Nk] fp32 CUDA -> [B,Cv,Nq].  q / k may also be `Packed` operands
     (inference path): forward only."""
+    if ops.STOCK_TORCH:
+        return _attend_stock(q, k, v, scale)
     if isinstance(q, Packed) and q.holder is not None:
         return _AttendPacked.apply(q.token, k.token, v, q.holder, k.holder, float(scale))
     if isinstance(q, Packed):
@@ -153,6 +162,8 @@ def attend(q, k, v, scale, precision="fp16"):
 
 def raw_correlation(q, k, scale):
     """`return_corr=True` path (correspondence.py:305-306): scaled logits [B,Nq,Nk]."""
+    if ops.STOCK_TORCH:
+        return torch.matmul(q.permute(0, 2, 1), k) * scale
     q16 = q.t if isinstance(q, Packed) else ops.pack_rows(q.contiguous())
     k16 = k.t if isinstance(k, Packed) else ops.pack_rows(k.contiguous())
     return ops.gemm_f16(q16, k16, alpha=scale)
@@ -167,7 +178,7 @@ FUSED_PROLOGUE = _os.environ.get("COCOS_FUSED_PROLOGUE", "1") != "0"
 def _operands(x, match_kernel, pono_c, precision, with_grad_ok=True):
     """theta / phi conv output -> normalised correlation operand.  Without autograd (inference) and with
     --PONO_C the whole prologue (unfold, centre, normalise, fp16 pack) is one fused kernel pair."""
-    fused = pono_c and precision == "fp16" \
+    fused = pono_c and precision == "fp16" and not ops.STOCK_TORCH \
         and match_kernel in (1, 3) and x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0 \
         and (x.shape[1] * match_kernel * match_kernel) % 64 == 0
     if fused and not (torch.is_grad_enabled() and x.requires_grad):

@@ -250,6 +250,14 @@ int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs,
                           static_cast<cudaStream_t>(stream));
 }
 
+int cocos_cast_op_bf16(const void* src, int src_Cs, int lo_off, void* dst, int dst_Cs, long long npix, void* stream) {
+  if (!src || !dst) {
+    set_error("cocos_cast_op_bf16: null pointer argument");
+    return -1;
+  }
+  return cast_op_bf16_launch(src, src_Cs, lo_off, dst, dst_Cs, npix, static_cast<cudaStream_t>(stream));
+}
+
 int cocos_maxpool2_nhwc_fwd(const void* x, void* y, int B, int Cs, int Ho, int Wo, void* stream) {
   if (!x || !y) {
     set_error("cocos_maxpool2_nhwc_fwd: null pointer argument");

@@ -217,19 +217,37 @@ __global__ void __launch_bounds__(256) spade_mod_nhwc_bwd_kernel(const SpadeBwd 
 }
 
 // ----------------------------------------------------------------------------------------------- instance norm
-// stats[b][c] = {sum, sumsq} over the H*W pixels; blockDim (32 channels-quads?, 8): thread x owns 4 channels.
-// grid (pixel chunks, channel groups of 128, B); partial sums land with atomics (stats zeroed by the launcher).
+// Common shape of the four kernels: blockDim = (TX <= 32 channel quads, 8 pixel lanes); a thread owns 4 channels
+// (c = (blockIdx.y * TX + tx) * 4) of one image, loads its per-channel coefficients ONCE and walks a pixel range with
+// stride 8, so the inner loop is loads / FMAs / stores only.  TX is chosen so that the channel groups are evenly
+// filled (C = 408: 4 groups of 26 quads instead of 3 full + 1 with 6).  grid (pixel chunks, channel groups, B).
+struct Coef4 {
+  float mean[4], rstd[4];
+};
+__device__ __forceinline__ Coef4 load_coef4(const float* __restrict__ stats, int b, int C, int c, float inv, float eps) {
+  Coef4 k;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(b) * C + c + j) * 2);
+    k.mean[j] = st.x * inv;
+    k.rstd[j] = rsqrtf(fmaxf(st.y * inv - k.mean[j] * k.mean[j], 0.f) + eps);
+  }
+  return k;
+}
+
+// stats[b][c] = {sum, sumsq} over the H*W pixels; partial sums land with atomics (stats zeroed by the launcher).
 __global__ void __launch_bounds__(256)
 in_stats_nhwc_kernel(const void* __restrict__ x, int kind, int Cs, int C, int HW, int pix_per_block,
                      float* __restrict__ stats) {
   __shared__ float red[8][32][8];
   const int b = blockIdx.z;
-  const int c = blockIdx.y * 128 + threadIdx.x * 4;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const int p0 = blockIdx.x * pix_per_block;
   int p1 = p0 + pix_per_block;
   if (p1 > HW) p1 = HW;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
+#pragma unroll 4
     for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
       const float4 v = ld4(x, kind, (static_cast<size_t>(b) * HW + pix) * Cs + c);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
@@ -270,41 +288,35 @@ struct InstFwd {
   float eps;
 };
 
-// one thread per 4 channels of one (padded) output pixel
-__global__ void __launch_bounds__(256) inst_act_nhwc_fwd_kernel(const InstFwd p) {
+// walks the (padded) OUTPUT pixels: halo pixels re-read their mirror source
+__global__ void __launch_bounds__(256) inst_act_nhwc_fwd_kernel(const InstFwd p, int pix_per_block) {
   const int Hp = p.H + 2 * p.y_pad, Wp = p.W + 2 * p.y_pad;
-  const int n4 = p.C >> 2;
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= static_cast<long long>(p.B) * Hp * Wp * n4) return;
-  const int c = static_cast<int>(idx % n4) * 4;
-  const long long op = idx / n4;
-  const int b = static_cast<int>(op / (Hp * Wp));
-  const int r = static_cast<int>(op - static_cast<long long>(b) * Hp * Wp);
-  const int ho = r / Wp, wo = r - ho * Wp;
-  const int hs = reflect1(ho - p.y_pad, p.H), ws = reflect1(wo - p.y_pad, p.W);
-  const size_t spix = (static_cast<size_t>(b) * p.H + hs) * p.W + ws;
-  const float inv = 1.0f / (p.H * p.W);
+  const int b = blockIdx.z;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= p.C) return;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block;
+  if (p1 > Hp * Wp) p1 = Hp * Wp;
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
-  const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
-  float in[4] = {v.x, v.y, v.z, v.w}, out[4];
-  float rs[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p.res) {
-    const float4 t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
-    rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
+  const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / (p.H * p.W), p.eps);
+#pragma unroll 2
+  for (int op = p0 + threadIdx.y; op < p1; op += 8) {
+    const int ho = op / Wp, wo = op - ho * Wp;
+    const int hs = reflect1(ho - p.y_pad, p.H), ws = reflect1(wo - p.y_pad, p.W);
+    const size_t spix = (static_cast<size_t>(b) * p.H + hs) * p.W + ws;
+    const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.res) t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
+    float4 o;
+    o.x = lrelu((v.x - k.mean[0]) * k.rstd[0] + t.x, slope);
+    o.y = lrelu((v.y - k.mean[1]) * k.rstd[1] + t.y, slope);
+    o.z = lrelu((v.z - k.mean[2]) * k.rstd[2] + t.z, slope);
+    o.w = lrelu((v.w - k.mean[3]) * k.rstd[3] + t.w, slope);
+    const size_t yo = (static_cast<size_t>(b) * Hp * Wp + op) * p.y_Cs + c;
+    st4(p.y, p.y_kind, yo, o);
+    if (p.y_lo_off) st4(p.y, 1, yo + p.y_lo_off, lo4(o));
+    if (p.y2 && ho - p.y_pad == hs && wo - p.y_pad == ws) st4(p.y2, 3, spix * p.y2_Cs + c, o);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
-    const float mean = st[0] * inv;
-    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
-    const float z = (in[j] - mean) * rsqrtf(var + p.eps) + rs[j];
-    out[j] = lrelu(z, slope);
-  }
-  const float4 o = make_float4(out[0], out[1], out[2], out[3]);
-  const size_t yo = static_cast<size_t>(op) * p.y_Cs + c;
-  st4(p.y, p.y_kind, yo, o);
-  if (p.y_lo_off) st4(p.y, 1, yo + p.y_lo_off, lo4(o));
-  if (p.y2 && ho - p.y_pad == hs && wo - p.y_pad == ws) st4(p.y2, 3, spix * p.y2_Cs + c, o);
 }
 
 struct InstBwd {
@@ -323,12 +335,18 @@ struct InstBwd {
 };
 
 // dz for 4 channels of one source pixel (shared by both passes)
-__device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, int b, int h, int w, int c, float slope, float* z,
-                                            float* dz, float* u_neg_dy) {
-  const int Wp = p.W + 2 * p.dy_pad, Hp = p.H + 2 * p.dy_pad;
-  const size_t spix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
-  const Fold f = make_fold(h, w, p.H, p.W, p.dy_pad);
-  float4 d = folded4(p.dy, 2, f, static_cast<size_t>(b) * Hp * Wp, Wp, p.dy_Cs, c);
+__device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, int b, int pix, int c, float slope,
+                                            float* z, float* dz, float* u_neg_dy) {
+  const size_t spix = static_cast<size_t>(b) * p.H * p.W + pix;
+  float4 d;
+  if (p.dy_pad) {
+    const int Wp = p.W + 2 * p.dy_pad, Hp = p.H + 2 * p.dy_pad;
+    const int h = pix / p.W, w = pix - h * p.W;
+    const Fold f = make_fold(h, w, p.H, p.W, p.dy_pad);
+    d = folded4(p.dy, 2, f, static_cast<size_t>(b) * Hp * Wp, Wp, p.dy_Cs, c);
+  } else {
+    d = ld4(p.dy, 2, spix * p.dy_Cs + c);
+  }
   if (p.dy2) {
     const float4 t = ld4(p.dy2, 2, spix * p.dy2_Cs + c);
     d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
@@ -340,25 +358,21 @@ __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, int b, int h, int 
     rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
   }
   const float in[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
-  const float inv = 1.0f / (p.H * p.W);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
-    const float mean = st[0] * inv;
-    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
-    z[j] = (in[j] - mean) * rsqrtf(var + p.eps);
+    z[j] = (in[j] - k.mean[j]) * k.rstd[j];
     const float u = z[j] + rs[j];
     dz[j] = u > 0.f ? dd[j] : dd[j] * slope;
     u_neg_dy[j] = u > 0.f ? 0.f : dd[j] * u;
   }
 }
 
-// pass 1: bstats += {sum dz, sum dz*z}, dslope += sum dy*u*[u<=0]; grid (pixel chunks, channel groups of 128, B)
+// pass 1: bstats += {sum dz, sum dz*z}, dslope += sum dy*u*[u<=0]
 __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const InstBwd p, int pix_per_block) {
   __shared__ float red[8][32][8];
   __shared__ float red_s[8][32];
   const int b = blockIdx.z;
-  const int c = blockIdx.y * 128 + threadIdx.x * 4;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const int HW = p.H * p.W;
   const int p0 = blockIdx.x * pix_per_block;
   int p1 = p0 + pix_per_block;
@@ -366,10 +380,11 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
   if (c < p.C) {
+    const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / HW, p.eps);
+#pragma unroll 2
     for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
-      const int h = pix / p.W, w = pix - h * p.W;
       float z[4], dz[4], un[4];
-      inst_bwd_dz(p, b, h, w, c, slope, z, dz, un);
+      inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s[j] += dz[j];
@@ -401,52 +416,55 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
         }
       }
     }
-    if (p.dslope) {
+    if (p.dslope && threadIdx.x == 0) {  // (a block row can be narrower than a warp: no shuffles here)
       float t = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) t += red_s[k][threadIdx.x];
-      t = warp_sum(t);
-      if (threadIdx.x == 0) atomicAdd(p.dslope, t);
+      for (int k = 0; k < 8; ++k)
+        for (int xx = 0; xx < static_cast<int>(blockDim.x); ++xx) t += red_s[k][xx];
+      atomicAdd(p.dslope, t);
     }
   }
 }
 
 // pass 2: dx = rstd * (dz - mean(dz) - z * mean(dz*z)); dres = dz
-__global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const InstBwd p) {
-  const int n4 = p.C >> 2;
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= static_cast<long long>(p.B) * p.H * p.W * n4) return;
-  const int c = static_cast<int>(idx % n4) * 4;
-  const long long pixl = idx / n4;
-  const int b = static_cast<int>(pixl / (p.H * p.W));
-  const int r = static_cast<int>(pixl - static_cast<long long>(b) * p.H * p.W);
-  const int h = r / p.W, w = r - h * p.W;
+__global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const InstBwd p, int pix_per_block) {
+  const int b = blockIdx.z;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= p.C) return;
+  const int HW = p.H * p.W;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block;
+  if (p1 > HW) p1 = HW;
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
-  float z[4], dz[4], un[4], o[4];
-  inst_bwd_dz(p, b, h, w, c, slope, z, dz, un);
-  const float inv = 1.0f / (p.H * p.W);
+  const float inv = 1.0f / HW;
+  const Coef4 k = load_coef4(p.stats, b, p.C, c, inv, p.eps);
+  float m1[4], m2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float* st = p.stats + (static_cast<size_t>(b) * p.C + c + j) * 2;
-    const float* bs = p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2;
-    const float mean = st[0] * inv;
-    const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
-    o[j] = rsqrtf(var + p.eps) * (dz[j] - bs[0] * inv - z[j] * bs[1] * inv);
+    const float2 bs = *reinterpret_cast<const float2*>(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2);
+    m1[j] = bs.x * inv;
+    m2[j] = bs.y * inv;
   }
-  const size_t spix = static_cast<size_t>(pixl);
-  float4 t = make_float4(o[0], o[1], o[2], o[3]);
-  if (p.dx_acc) {
-    const float4 old = ld4(p.dx, 2, spix * p.dx_Cs + c);
-    t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-  }
-  st4(p.dx, 2, spix * p.dx_Cs + c, t);
-  if (p.dres) {
-    float4 t2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
-    if (p.dres_acc) {
-      const float4 old = ld4(p.dres, 2, spix * p.dres_Cs + c);
-      t2.x += old.x; t2.y += old.y; t2.z += old.z; t2.w += old.w;
+#pragma unroll 2
+  for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
+    float z[4], dz[4], un[4], o[4];
+    inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = k.rstd[j] * (dz[j] - m1[j] - z[j] * m2[j]);
+    const size_t spix = static_cast<size_t>(b) * HW + pix;
+    float4 t = make_float4(o[0], o[1], o[2], o[3]);
+    if (p.dx_acc) {
+      const float4 old = ld4(p.dx, 2, spix * p.dx_Cs + c);
+      t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
     }
-    st4(p.dres, 2, spix * p.dres_Cs + c, t2);
+    st4(p.dx, 2, spix * p.dx_Cs + c, t);
+    if (p.dres) {
+      float4 t2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      if (p.dres_acc) {
+        const float4 old = ld4(p.dres, 2, spix * p.dres_Cs + c);
+        t2.x += old.x; t2.y += old.y; t2.z += old.z; t2.w += old.w;
+      }
+      st4(p.dres, 2, spix * p.dres_Cs + c, t2);
+    }
   }
 }
 
@@ -474,6 +492,34 @@ act_bwd_nhwc_kernel(const void* __restrict__ dy, int dy_Cs, const void* __restri
   d.z = v.z > 0.f ? d.z : d.z * neg;
   d.w = v.w > 0.f ? d.w : d.w * neg;
   st4(dz, 2, static_cast<size_t>(pixl) * dz_Cs + c, d);
+}
+
+// ----------------------------------------------------------------------------------------------- fp16 -> bf16 operand
+// The backward-weights GEMM multiplies dY (bf16: gradients need the fp32 exponent range) with the activation X the
+// forward saved (fp16 [hi | lo]); tcgen05 cannot mix fp16 x bf16 operands, and converting X inside the GEMM kernel
+// costs a third of its throughput (profiles/r02_tapconv_bf16x.txt).  So X is converted here, once per tensor, in an
+// HBM-bound pass: dst[pix][c] = bf16(hi + lo), 8 channels (16 bytes) per thread, halo pixels included.
+__global__ void __launch_bounds__(256)
+cast_op_bf16_kernel(const uint16_t* __restrict__ src, int src_Cs, int lo_off, uint16_t* __restrict__ dst, int dst_Cs,
+                    long long npix) {
+  const int n8 = dst_Cs >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= npix * n8) return;
+  const int c = static_cast<int>(idx % n8) * 8;
+  const long long pix = idx / n8;
+  const uint4 hi = *reinterpret_cast<const uint4*>(src + pix * src_Cs + c);
+  uint4 lo = make_uint4(0u, 0u, 0u, 0u);
+  if (lo_off) lo = *reinterpret_cast<const uint4*>(src + pix * src_Cs + lo_off + c);
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+  uint4 o;
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(h[i]), b = __half22float2(l[i]);
+    ob[i] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+  }
+  *reinterpret_cast<uint4*>(dst + pix * dst_Cs + c) = o;
 }
 
 // ----------------------------------------------------------------------------------------------- 2x2 max pooling
@@ -675,23 +721,40 @@ struct PackW {
   void* dst; int rows, rows_alloc, Kc, ngroups, transposed, bf16;
   int8_t r[COCOS_TAPCONV_MAX_GROUPS], s[COCOS_TAPCONV_MAX_GROUPS], term[COCOS_TAPCONV_MAX_GROUPS];
 };
+// One block = a 32 (output channels) x 32 (input channels) tile of the filter, staged through shared memory: the fp32
+// source [Cout, Cin, KS, KS] is read in runs of 32*KS*KS contiguous floats (one per output channel); then each warp
+// owns destination rows and writes, per tap group, 32 consecutive 16-bit elements (lane = the contiguous index of the
+// destination: input channel for the plain layout, output channel for the transposed one).  dst is fully written
+// (zeros beyond the filter's extents: no memset).  grid (ceil(Kc or rows_alloc / 32) input, ... output tiles).
 __global__ void __launch_bounds__(256) pack_w_kernel(const PackW p) {
-  const long long Kt = static_cast<long long>(p.ngroups) * p.Kc;
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= p.rows_alloc * Kt) return;
-  const int row = static_cast<int>(idx / Kt);
-  const int k = static_cast<int>(idx - row * Kt);
-  const int g = k / p.Kc, c = k - g * p.Kc;
-  float v = 0.f;
-  const int nc = p.transposed ? p.Cout : p.Cin;
-  if (row < p.rows && c < nc) {
-    const int co = p.transposed ? c : row, ci = p.transposed ? row : c;
-    v = p.w[((static_cast<size_t>(co) * p.Cin + ci) * p.KS + p.r[g]) * p.KS + p.s[g]];
+  extern __shared__ float tile[];  // [32][32 * KS*KS + 1]
+  const int kk = p.KS * p.KS;
+  const int pitch = 32 * kk + 1;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int run = (p.Cin - ci0 < 32 ? p.Cin - ci0 : 32) * kk;  // contiguous floats per output channel (<= 0: none)
+  for (int co = warp; co < 32; co += 8) {
+    const bool ok = co0 + co < p.Cout;
+    const float* src = p.w + (static_cast<size_t>(co0 + co) * p.Cin + ci0) * kk;
+    for (int e = lane; e < 32 * kk; e += 32) tile[co * pitch + e] = (ok && e < run) ? src[e] : 0.f;
   }
-  uint16_t bits;
-  if (p.bf16) bits = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-  else bits = __half_as_ushort(__float2half_rn(p.term[g] ? lo16(v) : v));
-  static_cast<uint16_t*>(p.dst)[idx] = bits;
+  __syncthreads();
+  uint16_t* dst = static_cast<uint16_t*>(p.dst);
+  const size_t Kt = static_cast<size_t>(p.ngroups) * p.Kc;
+  // plain: row = co0 + r, column = ci0 + lane, element tile[r][lane];  transposed: row = ci0 + r, column = co0 + lane,
+  // element tile[lane][r]
+  const int row0 = p.transposed ? ci0 : co0, col = (p.transposed ? co0 : ci0) + lane;
+  if (col >= p.Kc) return;
+  for (int r = warp; r < 32; r += 8) {
+    if (row0 + r >= p.rows_alloc) break;
+    const float* t = p.transposed ? tile + lane * pitch + r * kk : tile + r * pitch + lane * kk;
+    uint16_t* d = dst + static_cast<size_t>(row0 + r) * Kt + col;
+    for (int g = 0; g < p.ngroups; ++g) {
+      const float v = t[p.r[g] * p.KS + p.s[g]];
+      d[static_cast<size_t>(g) * p.Kc] = p.bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v))
+                                                : __half_as_ushort(__float2half_rn(p.term[g] ? lo16(v) : v));
+    }
+  }
 }
 
 inline int blocks_for(long long n, int per) { return static_cast<int>((n + per - 1) / per); }
@@ -730,16 +793,19 @@ int spade_mod_nhwc_bwd_launch(const void* dy, int dy_Cs, const void* x, int x_ki
   return 0;
 }
 
-static int stats_grid(int HW, int C, int B, dim3* grid, int* ppb) {
-  const int cg = (C + 127) / 128;
-  // ~4 waves of blocks, at least 64 pixels per block
-  int chunks = (4 * 148 + cg * B - 1) / (cg * B);
+// grid / block of the instance-norm kernels: TX channel quads per block row (evenly filled groups), ~8 waves of
+// blocks, at least 64 pixels per block
+static void stats_grid(int HW, int C, int B, dim3* grid, dim3* block, int* ppb) {
+  const int c4 = (C + 3) / 4;
+  const int cg = (c4 + 31) / 32;
+  const int tx = (c4 + cg - 1) / cg;
+  int chunks = (8 * 148 + cg * B - 1) / (cg * B);
   const int max_chunks = (HW + 63) / 64;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   *ppb = (HW + chunks - 1) / chunks;
   *grid = dim3((HW + *ppb - 1) / *ppb, cg, B);
-  return 0;
+  *block = dim3(tx, 8);
 }
 
 int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, cudaStream_t stream) {
@@ -748,10 +814,10 @@ int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, 
     return -1;
   }
   COCOS_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * C, stream));
-  dim3 grid;
+  dim3 grid, block;
   int ppb;
-  stats_grid(HW, C, B, &grid, &ppb);
-  in_stats_nhwc_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, kind, Cs, C, HW, ppb, stats);
+  stats_grid(HW, C, B, &grid, &block, &ppb);
+  in_stats_nhwc_kernel<<<grid, block, 0, stream>>>(x, kind, Cs, C, HW, ppb, stats);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -768,8 +834,10 @@ int inst_act_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const float* s
   }
   InstFwd p{x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, y, y_kind, y_Cs, y_lo_off, y_pad,
             y2, y2_Cs, B, C, H, W, eps};
-  const long long n = static_cast<long long>(B) * (H + 2 * y_pad) * (W + 2 * y_pad) * (C / 4);
-  inst_act_nhwc_fwd_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  dim3 grid, block;
+  int ppb;
+  stats_grid((H + 2 * y_pad) * (W + 2 * y_pad), C, B, &grid, &block, &ppb);
+  inst_act_nhwc_fwd_kernel<<<grid, block, 0, stream>>>(p, ppb);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -788,13 +856,12 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
   InstBwd p{dy, dy_Cs, dy_pad, dy2, dy2_Cs, x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, bstats,
             dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C, H, W, eps};
   COCOS_CUDA_CHECK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * B * C, stream));
-  dim3 grid;
+  dim3 grid, block;
   int ppb;
-  stats_grid(H * W, C, B, &grid, &ppb);
-  inst_act_nhwc_bwd_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(p, ppb);
+  stats_grid(H * W, C, B, &grid, &block, &ppb);
+  inst_act_nhwc_bwd_stats_kernel<<<grid, block, 0, stream>>>(p, ppb);
   COCOS_CUDA_CHECK(cudaGetLastError());
-  const long long n = static_cast<long long>(B) * H * W * (C / 4);
-  inst_act_nhwc_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  inst_act_nhwc_bwd_apply_kernel<<<grid, block, 0, stream>>>(p, ppb);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -842,6 +909,19 @@ int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
   nhwc_unpack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, kind, Cs, c_lo, C, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f,
                                                         acc);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int cast_op_bf16_launch(const void* src, int src_Cs, int lo_off, void* dst, int dst_Cs, long long npix,
+                        cudaStream_t stream) {
+  if (npix <= 0 || dst_Cs <= 0 || (dst_Cs % 8) || (src_Cs % 8) || (lo_off % 8) || lo_off < 0 ||
+      (lo_off ? lo_off : src_Cs) < dst_Cs || (lo_off && lo_off + dst_Cs > src_Cs)) {
+    set_error("cast_op_bf16: bad arguments (src_Cs=%d lo_off=%d dst_Cs=%d npix=%lld)", src_Cs, lo_off, dst_Cs, npix);
+    return -1;
+  }
+  cast_op_bf16_kernel<<<blocks_for(npix * (dst_Cs / 8), 256), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(src), src_Cs, lo_off, static_cast<uint16_t*>(dst), dst_Cs, npix);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -906,8 +986,14 @@ int pack_w_launch(const float* w, int Cout, int Cin, int KS, void* dst, int rows
     }
     p.r[g] = r[g]; p.s[g] = s[g]; p.term[g] = term[g];
   }
-  const long long n = static_cast<long long>(rows_alloc) * ngroups * Kc;
-  pack_w_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p);
+  // the grid covers the padded extents of dst: rows_alloc x Kc (zeros beyond the filter)
+  const int n_in = transposed ? rows_alloc : Kc, n_out = transposed ? Kc : rows_alloc;
+  const size_t smem = sizeof(float) * 32 * (32 * KS * KS + 1);
+  if (smem > 48 * 1024) {
+    COCOS_CUDA_CHECK(cudaFuncSetAttribute(pack_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+  }
+  pack_w_kernel<<<dim3((n_in + 31) / 32, (n_out + 31) / 32), dim3(32, 8), smem, stream>>>(p);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -66,3 +66,18 @@ def create_dataloader(opt, seed=0):
     gen.manual_seed(seed)
     return torch.utils.data.DataLoader(ds, batch_size=opt.batchSize, shuffle=not opt.serial_batches,
                                        num_workers=0, drop_last=opt.isTrain, generator=gen)
+
+
+def seeded_vgg_state_dict(seed=7):
+    """Deterministic stand-in for models/vgg19_conv.pth (pix2pix_model.py:30 loads it; not redistributable and not in
+    the reference tree): He-normal conv weights, zero bias.  Same recipe as oracle/ref_harness.py uses for the
+    reference side of the goldens."""
+    from .nets import VGG19_feature_color_torchversion
+    g = torch.Generator().manual_seed(seed)
+    sd = VGG19_feature_color_torchversion().state_dict()
+    for key, v in sd.items():
+        if key.endswith("weight"):
+            v.copy_(torch.randn(v.shape, generator=g) * (2.0 / v[0].numel()) ** 0.5)
+        else:
+            v.zero_()
+    return sd

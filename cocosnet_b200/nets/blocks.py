@@ -48,7 +48,7 @@ def conv_apply(conv, x):
     """`conv(x)` for an nn.Conv2d (possibly wrapped by spectral_norm / equal_lr): stride-1 3x3 / 1x1 convolutions
     run their forward on the tcgen05 implicit-GEMM kernel (K2, fp16 operands / fp32 accumulate, TF32-class
     precision); anything else, or `COCOS_NATIVE_CONV=0`, falls back to the module (cuDNN)."""
-    if (_ops.NATIVE_CONV and not _STRICT[0] and isinstance(conv, nn.Conv2d) and x.is_cuda and x.dtype == torch.float32
+    if (_ops.NATIVE_CONV and not _ops.STOCK_TORCH and not _STRICT[0] and isinstance(conv, nn.Conv2d) and x.is_cuda and x.dtype == torch.float32
             and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.kernel_size in ((3, 3), (1, 1)) and conv.padding_mode == "zeros"
             and conv.padding in ((0, 0), (conv.kernel_size[0] // 2,) * 2) and conv.out_channels >= 16):
@@ -159,7 +159,7 @@ def norm_act(layer, x, slope=None):
     if isinstance(layer, nn.Sequential) and len(layer) == 2 and isinstance(layer[1], nn.InstanceNorm2d) \
             and not layer[1].affine and not layer[1].track_running_stats:
         y = conv_apply(layer[0], x)
-        if y.is_cuda and y.dtype == torch.float32:
+        if y.is_cuda and y.dtype == torch.float32 and not _ops.STOCK_TORCH:
             return _ops.inst_act(y, 1.0 if slope is None else slope, layer[1].eps)
         y = layer[1](y)
     else:
@@ -206,14 +206,14 @@ class SPADE(nn.Module):
         b = torch.cat((self.mlp_gamma.bias, self.mlp_beta.bias), 0)
         if actv.dim() == 4 and actv.is_contiguous(memory_format=torch.channels_last) and not actv.is_contiguous():
             return F.conv2d(actv, w.contiguous(memory_format=torch.channels_last), b)
-        if _ops.NATIVE_CONV and not _STRICT[0] and actv.is_cuda and actv.dtype == torch.float32 and w.shape[2] in (1, 3):
+        if _ops.NATIVE_CONV and not _ops.STOCK_TORCH and not _STRICT[0] and actv.is_cuda and actv.dtype == torch.float32 and w.shape[2] in (1, 3):
             return _ops.conv_native(actv, w, b, pre_padded=True)
         return F.conv2d(actv, w, b)
 
     def forward(self, x, segmap, leaky=None, pad=0):
         """norm(x) * (1 + gamma) + beta [-> leaky_relu] [-> reflection pad]."""
         gb = self.gamma_beta(x, segmap)
-        if self.pono and x.is_cuda and x.dtype == torch.float32:
+        if self.pono and x.is_cuda and x.dtype == torch.float32 and not _ops.STOCK_TORCH:
             # PONO + modulation + activation + reflection pad: one fused sm_100a kernel each way
             return _ops.spade_mod(x, gb, pad=pad, slope=1.0 if leaky is None else leaky)
         gamma, beta = gb.chunk(2, dim=1)

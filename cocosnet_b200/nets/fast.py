@@ -87,7 +87,8 @@ class Pyramid:
 # ------------------------------------------------------------------------------------------------ SPADE blocks
 def enabled():
     import os
-    return os.environ.get("COCOS_NHWC", "1") != "0"
+    from .. import ops
+    return os.environ.get("COCOS_NHWC", "1") != "0" and not ops.STOCK_TORCH
 
 
 def _dev_ok(t):
@@ -374,7 +375,7 @@ def _d_chain(tp, ps, layers, x, emit_all, emit_last=False, first_w=None):
     return outs
 
 
-def discriminator_forward(net, sem, fake, real):
+def discriminator_forward(net, sem, fake, real, need_feats=True):
     """MultiscaleDiscriminator.forward (discriminator.py:56-69) on cat([sem | fake], [sem | real]) -- the batch
     pix2pix_model.py:299-304 builds -- without building it: returns (pred_fake, pred_real) as divide_pred does
     (pix2pix_model.py:320-333).  The label map and the two images are packed straight into the fp16 NHWC input of the
@@ -382,7 +383,8 @@ def discriminator_forward(net, sem, fake, real):
     channels are permuted to match).  In the generator step (fake carries a gradient) the fake half is recorded and the
     real half runs without a tape; in the discriminator step both halves are one batch."""
     opt = net.opt
-    keep_feats = not opt.no_ganFeat_loss
+    # the intermediate features only feed the feature-matching loss of the generator step (pix2pix_model.py:233-242)
+    keep_feats = need_feats and not opt.no_ganFeat_loss
     B, ns, ni = sem.shape[0], sem.shape[1], fake.shape[1]
     need_dx = fake.requires_grad and torch.is_grad_enabled()
     halves = [(fake, True), (real, False)] if need_dx else [(None, False)]

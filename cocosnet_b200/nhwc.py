@@ -29,10 +29,11 @@ def round_up(x, m):
 class NT:
     """NHWC activation: t [B, H + 2*pad, W + 2*pad, Cs]; C logical channels (the rest of Cs is zero / lo terms);
     lo = channel offset of the fp16 residual term of a 2-term split operand (0: none)."""
-    __slots__ = ("t", "kind", "C", "pad", "lo")
+    __slots__ = ("t", "kind", "C", "pad", "lo", "bf")
 
     def __init__(self, t, kind, C, pad=0, lo=0):
         self.t, self.kind, self.C, self.pad, self.lo = t, kind, C, pad, lo
+        self.bf = None  # bf16 copy for the backward-weights GEMM (as_bf16), made at most once
 
     B = property(lambda s: s.t.shape[0])
     H = property(lambda s: s.t.shape[1] - 2 * s.pad)
@@ -212,6 +213,10 @@ class NativeBackend:
         _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, c_lo, c_span,
                                             hs, ws, dst.H, dst.W, f, dst.pad, _stream()), "cocos_nhwc_pack")
 
+    def cast_bf16(self, x, dst):
+        _lib.check(self.lib.cocos_cast_op_bf16(x.t.data_ptr(), x.Cs, x.lo, dst.t.data_ptr(), dst.Cs,
+                                               x.t.numel() // x.Cs, _stream()), "cocos_cast_op_bf16")
+
     def maxpool_fwd(self, x, y):
         _lib.check(self.lib.cocos_maxpool2_nhwc_fwd(x.t.data_ptr(), y.t.data_ptr(), x.B, x.Cs, y.H, y.W, _stream()),
                    "cocos_maxpool2_nhwc_fwd")
@@ -282,6 +287,20 @@ def pack_into(src, dst, b_lo=0, c_lo=0, c_span=0, f=1):
 
 def batch_view(x, lo, hi):
     return NT(x.t[lo:hi], x.kind, x.C, x.pad, x.lo)
+
+
+def as_bf16(x):
+    """fp16 operand (hi [+ lo]) -> bf16 NT of the same geometry (halo included): the X operand of conv_wgrad.  Cached on
+    the NT: an activation that feeds several convolutions (the SPADE condition of one resolution) is converted once."""
+    if x.kind == BF16:
+        return x
+    assert x.kind == F16
+    if x.bf is None:
+        cs = x.lo if x.lo else x.Cs
+        out = NT(backend().empty(tuple(x.t.shape[:3]) + (cs,), BF16, x.t.device), BF16, x.C, x.pad)
+        backend().cast_bf16(x, out)
+        x.bf = out
+    return x.bf
 
 
 def maxpool2(x):
@@ -372,9 +391,17 @@ def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=Non
     return out
 
 
+import os as _os
+
+# X of the backward-weights GEMM converted to bf16 by a separate HBM-bound pass (0: inside the GEMM kernel, A/B runs)
+WGRAD_BF16_X = _os.environ.get("COCOS_WGRAD_BF16_X", "1") != "0"
+
+
 def conv_wgrad(dy, x, ks, stride=1, padding=0):
     """Backward-weights: dy NT bf16, x the NT the forward read (fp16, or bf16) -> dW fp32 [Cout, Cin, KS, KS]."""
     assert dy.kind == BF16 and dy.pad == 0 and x.kind in (F16, BF16)
+    if x.kind == F16 and WGRAD_BF16_X:
+        x = as_bf16(x)
     groups = plan_fwd(ks, padding, 0)
     cin, cout = x.C, dy.C
     cin_s = round_up(cin, 4)

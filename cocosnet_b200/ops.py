@@ -12,6 +12,9 @@ import os as _os
 
 # forward of stride-1 3x3 / 1x1 convolutions on the tcgen05 implicit-GEMM kernel (COCOS_NATIVE_CONV=0: cuDNN)
 NATIVE_CONV = _os.environ.get("COCOS_NATIVE_CONV", "1") != "0"
+# MEASUREMENT ONLY (bench.py's gpu_baseline leg): every hand-written kernel off, the mirror modules run the reference's
+# own torch expressions on cuDNN / cuBLAS -- "stock PyTorch on the same B200", the bar SURVEY.md 8d names.
+STOCK_TORCH = _os.environ.get("COCOS_STOCK_TORCH", "0") == "1"
 
 
 def _stream():

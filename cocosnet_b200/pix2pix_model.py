@@ -230,7 +230,8 @@ class Pix2PixModel(torch.nn.Module):
         # the reference marks the detached fake as requiring grad (pix2pix_model.py:285-286) although nothing
         # reads that gradient; leaving it off skips a useless input-gradient pass through D.
         fake_image = GforD["fake_image"].detach()
-        pred_fake, pred_real, _, _, _ = self.discriminate(input_semantics, fake_image, real_image)
+        # the hinge loss only reads the final predictions: no feature outputs in the D step
+        pred_fake, pred_real, _, _, _ = self.discriminate(input_semantics, fake_image, real_image, need_feats=False)
         return {"D_Fake": self.criterionGAN(pred_fake, False, for_discriminator=True) * self.opt.weight_gan,
                 "D_real": self.criterionGAN(pred_real, True, for_discriminator=True) * self.opt.weight_gan}
 
@@ -255,11 +256,12 @@ class Pix2PixModel(torch.nn.Module):
         gen = {"fake_image": self.net["netG"](input_semantics, warp_out=self._cbn_in(coor_out, input_semantics))}
         return {**gen, **coor_out}
 
-    def discriminate(self, input_semantics, fake_image, real_image):
+    def discriminate(self, input_semantics, fake_image, real_image, need_feats=True):
         from .nets import fast as _fast
         if _fast.discriminator_supported(self.net["netD"], input_semantics, real_image):
             # [semantics | image] pairs packed straight into the fp16 NHWC input of the PatchGANs (no fp32 concat)
-            pred_fake, pred_real = _fast.discriminator_forward(self.net["netD"], input_semantics, fake_image, real_image)
+            pred_fake, pred_real = _fast.discriminator_forward(self.net["netD"], input_semantics, fake_image, real_image,
+                                                               need_feats=need_feats)
             return pred_fake, pred_real, [], None, None
         fake_and_real = torch.cat([torch.cat([input_semantics, fake_image], dim=1),
                                    torch.cat([input_semantics, real_image], dim=1)], dim=0)

@@ -180,6 +180,12 @@ class Pix2PixTrainer:
         self._load_static(data)
         self._graph.replay()
 
+    def free_graph(self):
+        """Drop the captured iteration and its private memory pool (it is re-captured on the next run_step)."""
+        self._graph = self._static_in = None
+        self._graph_key_captured = None
+        self.g_losses, self.d_losses, self.out = {}, {}, {}
+
     def _graph_key(self, alpha):
         """Everything the iteration reads from Python (and therefore bakes into a captured graph): alpha -- only the
         gradient-reversal layer of the domain classifier reads it (correspondence.py:296-300, --weight_domainC > 0), it

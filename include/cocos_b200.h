@@ -276,6 +276,10 @@ int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int
  * image), 1) of pix2pix_model.py:301-302 without the concatenated tensor. */
 int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
                     int Hs, int Ws, int H, int W, int f, int pad, void* stream);
+/* fp16 operand [npix, src_Cs] (hi at channels [0, dst_Cs), optional lo term at lo_off) -> bf16 [npix, dst_Cs] =
+ * bf16(hi + lo): the X operand of cocos_tapwgrad (the weight-gradient half of autograd's convolution_backward),
+ * converted once per tensor instead of inside the GEMM.  Channel counts are multiples of 8. */
+int cocos_cast_op_bf16(const void* src, int src_Cs, int lo_off, void* dst, int dst_Cs, long long npix, void* stream);
 /* nn.MaxPool2d(2, 2) of the VGG19 feature net (correspondence.py:84-100) over fp16 NHWC [B, 2*Ho, 2*Wo, Cs] ->
  * [B, Ho, Wo, Cs] and its backward (dy / dx bf16, the gradient goes to the first maximum in scan order). */
 int cocos_maxpool2_nhwc_fwd(const void* x, void* y, int B, int Cs, int Ho, int Wo, void* stream);

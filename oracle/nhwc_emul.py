@@ -249,6 +249,11 @@ class EmulBackend:
         if dst.lo:
             dst.t[..., dst.lo + c_lo:dst.lo + c_lo + span] = self._pad_reflect(full - hi, dst.pad).to(dst.t.dtype)
 
+    def cast_bf16(self, x, dst):
+        cs = dst.t.shape[3]
+        v = x.t.float()[..., :cs] + (x.t.float()[..., x.lo:x.lo + cs] if x.lo else 0)
+        dst.t.copy_(v.to(dst.t.dtype))
+
     def maxpool_fwd(self, x, y):
         B, H, W, Cs = x.t.shape
         y.t.copy_(x.t.reshape(B, H // 2, 2, W // 2, 2, Cs).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 4, Cs)

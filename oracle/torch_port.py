@@ -43,14 +43,6 @@ def cpu_reference_mode():
 
 
 def seeded_vgg_state_dict(seed=7):
-    """Deterministic stand-in for models/vgg19_conv.pth (not redistributable / not in the
-    reference tree): He-normal conv weights, zero bias.  Same recipe as ref_harness."""
-    from cocosnet_b200.nets import VGG19_feature_color_torchversion
-    g = torch.Generator().manual_seed(seed)
-    sd = VGG19_feature_color_torchversion().state_dict()
-    for key, v in sd.items():
-        if key.endswith("weight"):
-            v.copy_(torch.randn(v.shape, generator=g) * (2.0 / v[0].numel()) ** 0.5)
-        else:
-            v.zero_()
-    return sd
+    """The seeded stand-in for models/vgg19_conv.pth lives in the product package (cocosnet_b200/data.py)."""
+    from cocosnet_b200.data import seeded_vgg_state_dict as f
+    return f(seed)

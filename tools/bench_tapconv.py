@@ -40,7 +40,8 @@ def timeit(fn, iters=10):
 
 
 def main():
-    print("%-30s %10s %10s %10s   (ms, TFLOP/s algorithmic; weight packing included in every call)" % ("layer", "fwd", "dgrad", "wgrad"))
+    print("%-30s %10s %10s %10s %10s  (ms, TFLOP/s algorithmic; weight packing included in every call; wgrad_bf16x = "
+          "backward-weights with X already bf16: no in-kernel fp16->bf16 conversion)" % ("layer", "fwd", "dgrad", "wgrad", "wgrad_bf16x"))
     for name, ks, stride, padding, cin, cout, b, h, w, halo in SHAPES:
         split = "split" in name
         g = torch.Generator(device="cuda").manual_seed(0)
@@ -54,8 +55,10 @@ def main():
         t_f = timeit(lambda: nhwc.conv(xin, wt, None, stride=stride, padding=padding, out_kind=nhwc.F32 if split else nhwc.F16))
         t_d = timeit(lambda: nhwc.conv_dgrad(dy, wt, (hin, win), stride=stride, padding=padding, in_pad=halo))
         t_w = timeit(lambda: nhwc.conv_wgrad(dy, xin, ks, stride=stride, padding=padding))
-        print("%-30s %5.3f/%4.0f %5.3f/%4.0f %5.3f/%4.0f" % (name, t_f, flops / t_f / 1e9, t_d, flops / t_d / 1e9, t_w,
-                                                            flops / t_w / 1e9))
+        xb = nhwc.pack(x, nhwc.BF16, pad=halo)
+        t_wb = timeit(lambda: nhwc.conv_wgrad(dy, xb, ks, stride=stride, padding=padding))
+        print("%-30s %5.3f/%4.0f %5.3f/%4.0f %5.3f/%4.0f %5.3f/%4.0f" % (name, t_f, flops / t_f / 1e9, t_d, flops / t_d / 1e9,
+                                                                        t_w, flops / t_w / 1e9, t_wb, flops / t_wb / 1e9))
 
 
 if __name__ == "__main__":
