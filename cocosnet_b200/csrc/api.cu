@@ -184,15 +184,24 @@ int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb
                                    slope, eps, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_pono_stats_nhwc(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,
+                          void* stream) {
+  if (!x || !mean || !rstd) {
+    set_error("cocos_pono_stats_nhwc: null pointer argument");
+    return -1;
+  }
+  return pono_stats_nhwc_launch(x, kind, Cs, C, npix, eps, mean, rstd, static_cast<cudaStream_t>(stream));
+}
+
 int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
-                             int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
-                             int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
-                             void* stream) {
+                             int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx,
+                             int dx_Cs, int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad,
+                             float slope, void* stream) {
   if (!dy || !x || !gb || !mean || !rstd || !dx || !dgb) {
     set_error("cocos_spade_mod_nhwc_bwd: null pointer argument");
     return -1;
   }
-  return spade_mod_nhwc_bwd_launch(dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, mean, rstd, dx, dx_Cs, dx_acc, dgb,
+  return spade_mod_nhwc_bwd_launch(dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, gb_W, mean, rstd, dx, dx_Cs, dx_acc, dgb,
                                    dgb_Cs, B, C, H, W, pad, slope, static_cast<cudaStream_t>(stream));
 }
 

@@ -76,8 +76,10 @@ int tapwgrad_launch(const cocos_tapwgrad_desc* d, cudaStream_t stream);
 int spade_mod_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
                               int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
                               float slope, float eps, cudaStream_t stream);
+int pono_stats_nhwc_launch(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,
+                           cudaStream_t stream);
 int spade_mod_nhwc_bwd_launch(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
-                              int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
+                              int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx, int dx_Cs,
                               int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
                               cudaStream_t stream);
 int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, float* stats, cudaStream_t stream);

@@ -125,10 +125,39 @@ __global__ void __launch_bounds__(256) spade_mod_nhwc_fwd_kernel(const SpadeFwd 
   }
 }
 
+// per-pixel PONO statistics for the SPADE epilogue of the tap convolution: one warp per pixel, two passes (L1-resident)
+__global__ void __launch_bounds__(256)
+pono_stats_nhwc_kernel(const void* __restrict__ x, int kind, int Cs, int C, long long npix, float eps,
+                       float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const size_t xo = static_cast<size_t>(pix) * Cs;
+  const int n4 = C >> 2;
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = ld4(x, kind, xo + 4 * i);
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(sum) / C;
+  float ss = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = ld4(x, kind, xo + 4 * i);
+    const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (C - 1) + eps);
+  if (lane == 0) {
+    mean_out[pix] = mean;
+    rstd_out[pix] = rstd;
+  }
+}
+
 struct SpadeBwd {
   const void* dy; int dy_Cs;            // bf16 [B, H+2p, W+2p, dy_Cs]
   const void* x; int x_kind, x_Cs;
   const void* gb; int gb_kind, gb_Cs;
+  int gb_W;                             // 0: gb / dgb = [gamma | beta]; W: per 2W channels [gamma of W | beta of W]
   const float* mean; const float* rstd;
   void* dx; int dx_Cs, dx_acc;          // bf16 [B,H,W,dx_Cs]; dx_acc: add to what is there
   void* dgb; int dgb_Cs;                // bf16 [B,H,W,dgb_Cs]: d gamma [0,C), d beta [C,2C)
@@ -180,18 +209,21 @@ __global__ void __launch_bounds__(256) spade_mod_nhwc_bwd_kernel(const SpadeBwd 
   const int n4 = p.C >> 2;
   const float mean = p.mean[spix], rstd = p.rstd[spix];
   float s1 = 0.f, s2 = 0.f;
+  // channel c -> position of gamma_c (beta_c is `boff` further) in gb / dgb
+  const int boff = p.gb_W ? p.gb_W : p.C;
   for (int i = lane; i < n4; i += 32) {
+    const int gi = p.gb_W ? ((4 * i) / p.gb_W) * 2 * p.gb_W + (4 * i) % p.gb_W : 4 * i;
     float4 d = folded4(p.dy, 2, f, img, Wp, p.dy_Cs, 4 * i);
     const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
-    const float4 g = ld4(p.gb, p.gb_kind, go + 4 * i), be = ld4(p.gb, p.gb_kind, go + p.C + 4 * i);
+    const float4 g = ld4(p.gb, p.gb_kind, go + gi), be = ld4(p.gb, p.gb_kind, go + gi + boff);
     const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd, xh2 = (v.z - mean) * rstd,
                 xh3 = (v.w - mean) * rstd;
     d.x = fmaf(xh0, 1.0f + g.x, be.x) > 0.f ? d.x : d.x * p.slope;
     d.y = fmaf(xh1, 1.0f + g.y, be.y) > 0.f ? d.y : d.y * p.slope;
     d.z = fmaf(xh2, 1.0f + g.z, be.z) > 0.f ? d.z : d.z * p.slope;
     d.w = fmaf(xh3, 1.0f + g.w, be.w) > 0.f ? d.w : d.w * p.slope;
-    st4(p.dgb, 2, spix * p.dgb_Cs + 4 * i, make_float4(d.x * xh0, d.y * xh1, d.z * xh2, d.w * xh3));
-    st4(p.dgb, 2, spix * p.dgb_Cs + p.C + 4 * i, d);
+    st4(p.dgb, 2, spix * p.dgb_Cs + gi, make_float4(d.x * xh0, d.y * xh1, d.z * xh2, d.w * xh3));
+    st4(p.dgb, 2, spix * p.dgb_Cs + gi + boff, d);
     const float e0 = d.x * (1.0f + g.x), e1 = d.y * (1.0f + g.y), e2 = d.z * (1.0f + g.z), e3 = d.w * (1.0f + g.w);
     s1 += (e0 + e1) + (e2 + e3);
     s2 += (e0 * xh0 + e1 * xh1) + (e2 * xh2 + e3 * xh3);
@@ -199,9 +231,10 @@ __global__ void __launch_bounds__(256) spade_mod_nhwc_bwd_kernel(const SpadeBwd 
   const float m1 = warp_sum(s1) / p.C, m2 = warp_sum(s2) / (p.C - 1);
   for (int i = lane; i < n4; i += 32) {
     // d beta was just written by this lane: dz = d beta, no need to fold again
-    const float4 d = ld4(p.dgb, 2, spix * p.dgb_Cs + p.C + 4 * i);
+    const int gi = p.gb_W ? ((4 * i) / p.gb_W) * 2 * p.gb_W + (4 * i) % p.gb_W : 4 * i;
+    const float4 d = ld4(p.dgb, 2, spix * p.dgb_Cs + gi + boff);
     const float4 v = ld4(p.x, p.x_kind, xo + 4 * i);
-    const float4 g = ld4(p.gb, p.gb_kind, go + 4 * i);
+    const float4 g = ld4(p.gb, p.gb_kind, go + gi);
     float4 t;
     t.x = rstd * (d.x * (1.0f + g.x) - m1 - (v.x - mean) * rstd * m2);
     t.y = rstd * (d.y * (1.0f + g.y) - m1 - (v.y - mean) * rstd * m2);
@@ -777,16 +810,28 @@ int spade_mod_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const void* g
   return 0;
 }
 
+int pono_stats_nhwc_launch(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,
+                           cudaStream_t stream) {
+  if (npix <= 0 || C < 4 || (C % 4) || (Cs % 4) || Cs < C || (kind != 1 && kind != 3)) {
+    set_error("pono_stats_nhwc: bad arguments (C=%d Cs=%d kind=%d npix=%lld)", C, Cs, kind, npix);
+    return -1;
+  }
+  pono_stats_nhwc_kernel<<<blocks_for(npix, 8), 256, 0, stream>>>(x, kind, Cs, C, npix, eps, mean, rstd);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int spade_mod_nhwc_bwd_launch(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
-                              int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
-                              int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
-                              cudaStream_t stream) {
+                              int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx,
+                              int dx_Cs, int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad,
+                              float slope, cudaStream_t stream) {
   if (B <= 0 || C < 4 || (C % 4) || H <= pad || W <= pad || pad < 0 || pad > 1 || (dy_Cs % 4) || (x_Cs % 4) ||
-      (gb_Cs % 4) || (dx_Cs % 4) || (dgb_Cs % 4) || (x_kind != 1 && x_kind != 3) || (gb_kind != 1 && gb_kind != 3)) {
+      (gb_Cs % 4) || (dx_Cs % 4) || (dgb_Cs % 4) || (x_kind != 1 && x_kind != 3) || (gb_kind != 1 && gb_kind != 3) ||
+      gb_W < 0 || (gb_W && ((gb_W % 4) || (C % gb_W)))) {
     set_error("spade_mod_nhwc_bwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, pad);
     return -1;
   }
-  SpadeBwd p{dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, mean, rstd, dx, dx_Cs, dx_acc, dgb, dgb_Cs,
+  SpadeBwd p{dy, dy_Cs, x, x_kind, x_Cs, gb, gb_kind, gb_Cs, gb_W, mean, rstd, dx, dx_Cs, dx_acc, dgb, dgb_Cs,
              B, C, H, W, pad, slope};
   spade_mod_nhwc_bwd_kernel<<<blocks_for(static_cast<long long>(B) * H * W, 8), 256, 0, stream>>>(p);
   COCOS_CUDA_CHECK(cudaGetLastError());

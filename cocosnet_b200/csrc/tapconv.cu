@@ -48,6 +48,7 @@ struct TapParams {
   int8_t dh[MAXG], dw[MAXG];
   int16_t coff[MAXG];
   // epilogue
+  const float* scale;
   const float* bias;
   const void* res;
   int res_kind, res_Cs;
@@ -56,6 +57,11 @@ struct TapParams {
   void* y;
   int y_kind, y_H, y_W, y_Cs, y_coff, y_lo_off, y_pad, y_reflect;
   int y_sh, y_sw, y_oh, y_ow;
+  // SPADE modulation epilogue (mod_W > 0): an N tile holds [gamma of mod_W channels | beta of the same channels]
+  int mod_W;
+  const void* mod_x; int mod_x_kind, mod_x_Cs;
+  const float* mod_mean; const float* mod_rstd;
+  void* gb; int gb_kind, gb_Cs;
 };
 
 struct TapBars {
@@ -230,6 +236,7 @@ tapconv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int yHp = p.y_H + 2 * p.y_pad, yWp = p.y_W + 2 * p.y_pad;
     const bool out16 = p.y_kind == 1 || p.y_kind == 2;
     const bool obf = p.y_kind == 2;
+    const float scale = p.scale ? __ldg(p.scale) : 1.0f;
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       int t = tile;
@@ -255,6 +262,87 @@ tapconv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_wait(smem_u32(&bars->acc_full[buf]), (local >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem + buf * BN + lane_sel;
+      if (p.mod_W) {
+        // ---- SPADE: y = reflect_pad(lrelu(PONO(x) * (1 + gamma) + beta)) straight from the gamma / beta accumulators
+        // (normalization.py:132-149 + architecture.py:73-74); the raw [gamma | beta] pair is stored too when the
+        // backward will need it.  Tile n_i covers channels [n_i * mod_W, (n_i + 1) * mod_W) of x / y.
+        const size_t spix = (static_cast<size_t>(b) * p.y_H + yh) * p.y_W + yw;
+        float mean = 0.f, rstd = 0.f;
+        if (ok) { mean = __ldg(p.mod_mean + spix); rstd = __ldg(p.mod_rstd + spix); }
+#pragma unroll 1
+        for (int c = 0; c < p.mod_W / 32; ++c) {
+          uint32_t rg[32], rb[32];
+          tmem_ld32(acc + c * 32, rg);
+          tmem_ld32(acc + p.mod_W + c * 32, rb);
+          tmem_wait_ld();
+          if (!ok) continue;
+          const int ch = n_i * p.mod_W + c * 32;        // channel of x / y
+          const int ng = n0 + c * 32, nbt = ng + p.mod_W;  // columns (= rows of the interleaved weight / bias)
+          float v[32], g[32], be[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            g[i] = __uint_as_float(rg[i]) * scale;
+            be[i] = __uint_as_float(rb[i]) * scale;
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              g[i] += __ldg(p.bias + ng + i);
+              be[i] += __ldg(p.bias + nbt + i);
+            }
+          }
+          if (p.gb) {
+            const size_t go = spix * p.gb_Cs;
+            if (p.gb_kind == 3) {
+              store32(static_cast<float*>(p.gb) + go + ng, g, 32, true);
+              store32(static_cast<float*>(p.gb) + go + nbt, be, 32, true);
+            } else {
+              store16(static_cast<uint16_t*>(p.gb) + go + ng, g, 32, true, false);
+              store16(static_cast<uint16_t*>(p.gb) + go + nbt, be, 32, true, false);
+            }
+          }
+          if (p.mod_x_kind == 3) {
+            const float4* xp = reinterpret_cast<const float4*>(static_cast<const float*>(p.mod_x) + spix * p.mod_x_Cs + ch);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = xp[q];
+              v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+          } else {
+            const uint4* xp = reinterpret_cast<const uint4*>(static_cast<const __half*>(p.mod_x) + spix * p.mod_x_Cs + ch);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t = xp[q];
+              const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                v[8 * q + 2 * e] = f.x; v[8 * q + 2 * e + 1] = f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float z = fmaf((v[i] - mean) * rstd, 1.0f + g[i], be[i]);
+            v[i] = z > 0.f ? z : z * p.slope;
+          }
+          float lo[32];
+          if (p.y_lo_off) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lo[i] = lo_of(v[i]);
+          }
+          for (int a = 0; a < nr; ++a)
+            for (int e = 0; e < nc; ++e) {
+              const size_t po = ((static_cast<size_t>(b) * yHp + rt[a]) * yWp + ct[e]) * p.y_Cs + ch;
+              store16(static_cast<uint16_t*>(p.y) + po, v, 32, true, false);
+              if (p.y_lo_off) store16(static_cast<uint16_t*>(p.y) + po + p.y_lo_off, lo, 32, true, false);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nb = n0 + c * 32;
@@ -266,7 +354,7 @@ tapconv_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const int n_ok = min(32, p.Cout - nb);
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * scale;
         if (p.bias) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -384,7 +472,7 @@ int tapconv_launch(const cocos_tapconv_desc* d, cudaStream_t stream) {
   p.tiles_b = (d->B + p.TB - 1) / p.TB;
   p.tiles_h = (d->H + p.TH - 1) / p.TH;
   p.tiles_w = (d->W + p.TW - 1) / p.TW;
-  const int BN = d->Cout > 128 ? 256 : 128;
+  const int BN = d->mod_W ? 2 * d->mod_W : (d->Cout > 128 ? 256 : 128);
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.num_tiles = p.tiles_b * p.tiles_h * p.tiles_w * p.tiles_n;
   p.a_stride = s; p.Ca = d->Ca; p.bf16 = d->bf16;
@@ -396,11 +484,25 @@ int tapconv_launch(const cocos_tapconv_desc* d, cudaStream_t stream) {
       return -1;
     }
   }
-  p.bias = d->bias; p.res = d->res; p.res_kind = d->res_kind; p.res_Cs = d->res_Cs;
+  p.scale = d->scale; p.bias = d->bias; p.res = d->res; p.res_kind = d->res_kind; p.res_Cs = d->res_Cs;
   p.act = d->act; p.slope = d->slope;
   p.y = d->y; p.y_kind = d->y_kind; p.y_H = d->y_H; p.y_W = d->y_W; p.y_Cs = d->y_Cs; p.y_coff = d->y_coff;
   p.y_lo_off = d->y_lo_off; p.y_pad = d->y_pad; p.y_reflect = d->y_reflect;
   p.y_sh = d->y_sh; p.y_sw = d->y_sw; p.y_oh = d->y_oh; p.y_ow = d->y_ow;
+  p.mod_W = d->mod_W; p.mod_x = d->mod_x; p.mod_x_kind = d->mod_x_kind; p.mod_x_Cs = d->mod_x_Cs;
+  p.mod_mean = d->mod_mean; p.mod_rstd = d->mod_rstd; p.gb = d->gb; p.gb_kind = d->gb_kind; p.gb_Cs = d->gb_Cs;
+  if (d->mod_W) {
+    const int C = d->Cout / 2;
+    if ((d->mod_W != 64 && d->mod_W != 128) || (d->Cout % (2 * d->mod_W)) || (d->mod_W == 64 && C != 64) || !d->mod_x ||
+        !d->mod_mean || !d->mod_rstd || (d->mod_x_kind != 1 && d->mod_x_kind != 3) || (d->mod_x_Cs % 8) || d->y_kind != 1 ||
+        (d->y_Cs % 8) || (d->y_lo_off % 8) || d->y_coff || d->res || d->act != 2 || d->y_sh != 1 || d->y_sw != 1 ||
+        d->y_oh || d->y_ow || d->H != d->y_H || d->W != d->y_W ||
+        (d->gb && ((d->gb_kind != 1 && d->gb_kind != 3) || (d->gb_Cs % 8) || d->gb_Cs < d->Cout))) {
+      set_error("tapconv: bad SPADE-epilogue descriptor (Cout=%d mod_W=%d x_kind=%d y_kind=%d act=%d)", d->Cout, d->mod_W,
+                d->mod_x_kind, d->y_kind, d->act);
+      return -1;
+    }
+  }
   if ((d->H - 1) * d->y_sh + d->y_oh >= d->y_H || (d->W - 1) * d->y_sw + d->y_ow >= d->y_W) {
     set_error("tapconv: output pixels fall outside y (%dx%d into %dx%d)", d->H, d->W, d->y_H, d->y_W);
     return -1;

@@ -128,7 +128,7 @@ class NoVGGCorrespondence(BaseNetwork):
         feat_seg = feature_normalize(self.adaptive_model_seg(seg_input, seg_input))
         feat_img = feature_normalize(self.adaptive_model_img(ref_img, ref_img))
         if opt.isTrain and opt.novgg_featpair > 0:
-            pair = feature_normalize(self.adaptive_model_img(real_img, real_img))
+            pair = feature_normalize(self.adaptive_model_img(real_img, real_img, loss_only=True))
             coor_out["loss_novgg_featpair"] = F.l1_loss(feat_seg, pair) * opt.novgg_featpair
         if opt.use_coordconv:
             feat_seg, feat_img = self.addcoords(feat_seg), self.addcoords(feat_img)

@@ -20,6 +20,27 @@ from ..nhwc import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, F16, F32
 
 
 # ------------------------------------------------------------------------------------------------ parameters
+from torch.nn.utils.spectral_norm import SpectralNorm as _SpectralNorm  # noqa: E402
+
+
+def _sn_weight_and_scale(m, hook):
+    """What torch.nn.utils.spectral_norm's pre-forward hook does (one power iteration on the persistent u / v in
+    training mode, sigma = u^T W v with u, v constant; normalization.py:30-31 wraps every generator / discriminator
+    conv with it) -- except for the last line, `weight = weight_orig / sigma`: returns (weight_orig, 1 / sigma)."""
+    weight = getattr(m, hook.name + "_orig")
+    u, v = getattr(m, hook.name + "_u"), getattr(m, hook.name + "_v")
+    wm = weight.reshape(weight.shape[0], -1)
+    if m.training:
+        with torch.no_grad():
+            for _ in range(hook.n_power_iterations):
+                v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=hook.eps, out=v)
+                u = F.normalize(torch.mv(wm, v), dim=0, eps=hook.eps, out=u)
+            if hook.n_power_iterations > 0:
+                u, v = u.clone(memory_format=torch.contiguous_format), v.clone(memory_format=torch.contiguous_format)
+    sigma = torch.dot(u, torch.mv(wm, v))
+    return weight, (1.0 / sigma).reshape(1)
+
+
 class ParamSet:
     """The tensors that become inputs of the boundary Function (conv weights after their spectral-norm / equal-lr
     pre-hooks ran -- exactly once per module per forward, like nn.Module.__call__ would) and their Params inside."""
@@ -35,23 +56,42 @@ class ParamSet:
     def conv(self, m):
         if ("w", id(m)) in self.slot:
             return
-        for hook in m._forward_pre_hooks.values():
-            hook(m, (None,))
-        self._add(("w", id(m)), m.weight)
+        sn = [h for h in m._forward_pre_hooks.values() if isinstance(h, _SpectralNorm)]
+        if len(sn) == 1 and len(m._forward_pre_hooks) == 1 and sn[0].dim == 0 and sn[0].name == "weight":
+            # spectral norm without ever forming weight_orig / sigma: the convolution kernels multiply their
+            # accumulators by 1/sigma (one scalar), the weight the tape packs and differentiates is weight_orig
+            w, inv_sigma = _sn_weight_and_scale(m, sn[0])
+            self._add(("w", id(m)), w)
+            self._add(("s", id(m)), inv_sigma)
+        else:
+            for hook in m._forward_pre_hooks.values():
+                hook(m, (None,))
+            self._add(("w", id(m)), m.weight)
         if m.bias is not None:
             self._add(("b", id(m)), m.bias)
 
     def spade(self, m):
-        """gamma and beta convs share their input: one conv with concatenated filters (gb = [gamma | beta])."""
+        """gamma and beta convs share their input: one conv with concatenated filters.  Row order: per 2W rows
+        [gamma of W channels | beta of the same] when the layer fits the SPADE epilogue of the convolution kernel
+        (nhwc.conv_spade), else [gamma | beta]."""
         self.conv(m.mlp_shared[1])
-        self._add(("w", id(m)), torch.cat((m.mlp_gamma.weight, m.mlp_beta.weight), 0))
-        self._add(("b", id(m)), torch.cat((m.mlp_gamma.bias, m.mlp_beta.bias), 0))
+        C = m.mlp_gamma.out_channels
+        W = nhwc.spade_interleave(C) if fused_spade() else 0
+        if W:
+            self._add(("w", id(m)), nhwc.interleave_rows(m.mlp_gamma.weight, m.mlp_beta.weight, W))
+            self._add(("b", id(m)), nhwc.interleave_rows(m.mlp_gamma.bias, m.mlp_beta.bias, W))
+        else:
+            self._add(("w", id(m)), torch.cat((m.mlp_gamma.weight, m.mlp_beta.weight), 0))
+            self._add(("b", id(m)), torch.cat((m.mlp_gamma.bias, m.mlp_beta.bias), 0))
 
     def tensor(self, key, t):
         self._add(("t", key), t)
 
     def bind(self, params):
         self.params = params
+        for (kind, key), i in self.slot.items():
+            if kind == "s":
+                params[self.slot[("w", key)]].scale = params[i]
 
     def w(self, m):
         return self.params[self.slot[("w", id(m))]]
@@ -91,6 +131,13 @@ def enabled():
     return os.environ.get("COCOS_NHWC", "1") != "0" and not ops.STOCK_TORCH
 
 
+def fused_spade():
+    """gamma / beta modulation + LeakyReLU + reflection halo in the epilogue of the gamma|beta convolution
+    (COCOS_FUSED_SPADE=0: convolution + separate modulation kernel, for A/B runs)."""
+    import os
+    return os.environ.get("COCOS_FUSED_SPADE", "1") != "0"
+
+
 def _dev_ok(t):
     """CUDA tensors on the native backend; anything on the emulation the CPU tests install."""
     return t.dtype == torch.float32 and (t.is_cuda or type(nhwc.backend()).__name__ != "NativeBackend")
@@ -123,6 +170,8 @@ def spade_norm(tp, ps, norm, x, pyr, mode, slope, pad):
     shared = norm.mlp_shared[1]
     actv = T.conv(tp, seg, ps.w(shared), ps.b(shared), act=ACT_RELU, out_kind=F16, out_pad=1, split_out=mode.split,
                   dx_ch=pyr.grad_ch, wsplit=mode.split)
+    if fused_spade() and nhwc.spade_interleave(C):
+        return T.spade_conv(tp, x, actv, ps.w(norm), ps.b(norm), C, pad, slope, mode.split, gb_kind=mode.raw)
     gb = T.conv(tp, actv, ps.w(norm), ps.b(norm), out_kind=mode.raw)
     return T.spade(tp, x, gb, C, pad, slope, mode.split)
 

@@ -100,9 +100,13 @@ class AdaptiveFeatureGenerator(BaseNetwork):
                 self.deeper1 = SPADEResnetBlock(4 * nf, 4 * nf, opt)
                 self.deeper2 = SPADEResnetBlock(4 * nf, 4 * nf, opt)
 
-    def forward(self, input, seg):
+    def forward(self, input, seg, loss_only=False):
+        """loss_only: the features only feed a loss term (the novgg_featpair pass over the real image,
+        correspondence.py:250-252), not the correlation: single-term operands are enough (the 2e-3 loss tolerance,
+        not the 1e-3 output bar that 1/temperature = 100 tightens for everything upstream of warp_out)."""
         if seg is input and _fast.adaptor_supported(self, input):
-            return _fast.adaptor_forward(self, input, precise=_fast.conv_precision(self.opt) != "fast")
+            return _fast.adaptor_forward(self, input,
+                                         precise=_fast.conv_precision(self.opt) != "fast" and not loss_only)
         with strict_convs(input.is_cuda and _fast.conv_precision(self.opt) != "fast"):
             return self._forward_modules(input, seg)
 

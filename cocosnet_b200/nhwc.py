@@ -94,14 +94,17 @@ def conv_out_size(n_in, ks, padding, stride):
 # ------------------------------------------------------------------------------------------------ native backend
 class _TapconvDesc(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("res", ctypes.c_void_p),
-                ("y", ctypes.c_void_p)] + \
+                ("y", ctypes.c_void_p), ("scale", ctypes.c_void_p)] + \
                [(n, ctypes.c_int) for n in ("B", "Hin", "Win", "Ca", "a_stride", "bf16", "H", "W", "Cout", "w_rows",
                                             "ngroups", "kchunks")] + \
                [("dh", ctypes.c_byte * MAXG), ("dw", ctypes.c_byte * MAXG), ("coff", ctypes.c_short * MAXG),
                 ("res_kind", ctypes.c_int), ("res_Cs", ctypes.c_int), ("act", ctypes.c_int),
                 ("slope", ctypes.c_float)] + \
                [(n, ctypes.c_int) for n in ("y_kind", "y_H", "y_W", "y_Cs", "y_coff", "y_lo_off", "y_pad", "y_reflect",
-                                            "y_sh", "y_sw", "y_oh", "y_ow")]
+                                            "y_sh", "y_sw", "y_oh", "y_ow")] + \
+               [("mod_W", ctypes.c_int), ("mod_x", ctypes.c_void_p), ("mod_x_kind", ctypes.c_int),
+                ("mod_x_Cs", ctypes.c_int), ("mod_mean", ctypes.c_void_p), ("mod_rstd", ctypes.c_void_p),
+                ("gb", ctypes.c_void_p), ("gb_kind", ctypes.c_int), ("gb_Cs", ctypes.c_int)]
 
 
 class _TapwgradDesc(ctypes.Structure):
@@ -140,6 +143,14 @@ class NativeBackend:
         """d: dict of the scalar descriptor fields + 'groups'."""
         desc = _TapconvDesc()
         desc.x, desc.w, desc.bias, desc.res, desc.y = _p(x), _p(w), _p(bias), _p(res), _p(y)
+        desc.scale = _p(d.get("scale"))
+        mod = d.get("mod")
+        if mod is not None:  # SPADE epilogue: x raw NT, mean, rstd, gb NT | None
+            mx, mean, rstd, gb = mod["x"], mod["mean"], mod["rstd"], mod["gb"]
+            desc.mod_W, desc.mod_x, desc.mod_x_kind, desc.mod_x_Cs = mod["W"], mx.t.data_ptr(), mx.kind, mx.Cs
+            desc.mod_mean, desc.mod_rstd = mean.data_ptr(), rstd.data_ptr()
+            if gb is not None:
+                desc.gb, desc.gb_kind, desc.gb_Cs = gb.t.data_ptr(), gb.kind, gb.Cs
         for k in ("B", "Hin", "Win", "Ca", "a_stride", "bf16", "H", "W", "Cout", "w_rows", "kchunks", "res_kind", "res_Cs",
                   "act", "y_kind", "y_H", "y_W", "y_Cs", "y_coff", "y_lo_off", "y_pad", "y_reflect", "y_sh", "y_sw",
                   "y_oh", "y_ow"):
@@ -177,9 +188,13 @@ class NativeBackend:
                                                      x.B, C, x.H, x.W, pad, float(slope), float(eps), _stream()),
                    "cocos_spade_mod_nhwc_fwd")
 
-    def spade_bwd(self, dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope):
+    def pono_stats(self, x, C, eps, mean, rstd):
+        _lib.check(self.lib.cocos_pono_stats_nhwc(x.t.data_ptr(), x.kind, x.Cs, C, x.t.numel() // x.Cs, float(eps),
+                                                  mean.data_ptr(), rstd.data_ptr(), _stream()), "cocos_pono_stats_nhwc")
+
+    def spade_bwd(self, dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope, gb_W=0):
         _lib.check(self.lib.cocos_spade_mod_nhwc_bwd(dy.t.data_ptr(), dy.Cs, x.t.data_ptr(), x.kind, x.Cs,
-                                                     gb.t.data_ptr(), gb.kind, gb.Cs, mean.data_ptr(), rstd.data_ptr(),
+                                                     gb.t.data_ptr(), gb.kind, gb.Cs, gb_W, mean.data_ptr(), rstd.data_ptr(),
                                                      dx.t.data_ptr(), dx.Cs, int(dx_acc), dgb.t.data_ptr(), dgb.Cs,
                                                      x.B, C, x.H, x.W, pad, float(slope), _stream()),
                    "cocos_spade_mod_nhwc_bwd")
@@ -338,9 +353,10 @@ def _pack_weight(weight, groups, rows, kc, transposed, bf16):
 
 
 def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kind=F16, out_pad=0, split_out=False,
-         res=None, nchw_out=None, nchw_coff=0, wsplit=None):
+         res=None, nchw_out=None, nchw_coff=0, wsplit=None, scale=None):
     """nn.Conv2d forward on the tap-convolution kernel.  x: NT fp16 (its tensor, halo included, IS the conv input;
-    `padding` is the module's zero padding).  Returns an NT of kind out_kind (op tensors: out_pad = 1 adds the
+    `padding` is the module's zero padding).  scale: 1-element fp32 device tensor multiplied into the accumulator
+    before the bias (spectral norm's 1/sigma: `weight` stays the un-normalised weight_orig).  Returns an NT of kind out_kind (op tensors: out_pad = 1 adds the
     reflection halo of the next conv, split_out the lo term), or writes fp32 NCHW into `nchw_out` (channels from
     nchw_coff) and returns it."""
     assert x.kind == F16, "forward operands are fp16"
@@ -353,7 +369,7 @@ def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out
     wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False)
     d = dict(B=x.B, Hin=hin, Win=win, Ca=x.Cs, a_stride=stride, bf16=0, H=h, W=w, Cout=cout, w_rows=rows_alloc,
              kchunks=kchunks, groups=groups, res_kind=res.kind if res else 0, res_Cs=res.Cs if res else 0, act=act,
-             slope=slope, y_H=h, y_W=w, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=1, y_sw=1, y_oh=0, y_ow=0)
+             slope=slope, scale=scale, y_H=h, y_W=w, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=1, y_sw=1, y_oh=0, y_ow=0)
     if res is not None:
         assert res.pad == 0 and res.H == h and res.W == w and res.C == cout
     if nchw_out is not None:
@@ -367,7 +383,53 @@ def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out
     return out
 
 
-def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=None):
+def spade_interleave(C):
+    """Width of the [gamma | beta] interleave of the SPADE-epilogue convolution for C modulated channels (0: the layer
+    does not fit the epilogue and runs as convolution + spade_mod_fwd)."""
+    return 128 if C % 128 == 0 else (64 if C == 64 else 0)
+
+
+def interleave_rows(gamma, beta, W):
+    """[C, ...] gamma rows and beta rows -> [2C, ...] ordered per 2W rows as [gamma of W channels | beta of the same]."""
+    C = gamma.shape[0]
+    parts = []
+    for c0 in range(0, C, W):
+        parts += [gamma[c0:c0 + W], beta[c0:c0 + W]]
+    return torch.cat(parts, 0)
+
+
+def conv_spade(actv, weight, bias, x, C, pad, slope, eps=1e-5, split_out=False, want_gb=True, gb_kind=F16, wsplit=None):
+    """SPADE (normalization.py:129-151) + the activation / ReflectionPad2d that follow it (architecture.py:73-74) as
+    ONE convolution launch: `weight` / `bias` are mlp_gamma and mlp_beta interleaved by interleave_rows, actv the
+    fp16 operand (relu(mlp_shared(seg)) with its reflection halo), x the raw activation to modulate.  The epilogue
+    normalises x per pixel (statistics from one pass of cocos_pono_stats_nhwc), modulates, applies the LeakyReLU and
+    writes the operand of the next convolution -- gamma / beta only reach HBM (as `gb`) when the backward needs them.
+    Returns (y op NT, gb NT | None, mean, rstd)."""
+    W = spade_interleave(C)
+    assert W and actv.kind == F16 and x.pad == 0 and x.C == C and weight.shape[0] == 2 * C and x.kind in (F16, F32)
+    cout, cin, ks, _ = weight.shape
+    assert cin == actv.C
+    hin, win = actv.t.shape[1], actv.t.shape[2]
+    h, w = conv_out_size(hin, ks, 0, 1), conv_out_size(win, ks, 0, 1)
+    assert (h, w) == (x.H, x.W)
+    be = backend()
+    mean = torch.empty((x.B, x.H, x.W), dtype=torch.float32, device=x.t.device)
+    rstd = torch.empty_like(mean)
+    be.pono_stats(x, C, eps, mean, rstd)
+    groups = plan_fwd(ks, 0, actv.lo, wsplit)
+    kchunks = (cin + 63) // 64
+    wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False)
+    y = new(x.B, h, w, C, F16, x.t.device, pad=pad, split=split_out, zero=False)
+    gb = new(x.B, h, w, 2 * C, gb_kind, x.t.device, zero=False) if want_gb else None
+    d = dict(B=x.B, Hin=hin, Win=win, Ca=actv.Cs, a_stride=1, bf16=0, H=h, W=w, Cout=cout, w_rows=rows_alloc,
+             kchunks=kchunks, groups=groups, res_kind=0, res_Cs=0, act=ACT_LRELU, slope=slope, scale=None, y_kind=F16,
+             y_H=h, y_W=w, y_Cs=y.Cs, y_coff=0, y_lo_off=y.lo, y_pad=pad, y_reflect=1 if pad else 0, y_sh=1, y_sw=1,
+             y_oh=0, y_ow=0, mod=dict(W=W, x=x, mean=mean, rstd=rstd, gb=gb))
+    be.tapconv(actv.t, wp, bias, None, y.t, d)
+    return y, gb, mean, rstd
+
+
+def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=None, scale=None):
     """Backward-data: dy NT bf16 [B,H,W,Cout] -> gradient w.r.t. the conv input tensor (halo included) as an NT bf16
     with pad = in_pad (the consumer folds the halo).  in_hw = (Hin, Win) of the input tensor incl. halo.
     c_lo / c_n: only input channels [c_lo, c_lo + c_n) are produced."""
@@ -385,7 +447,7 @@ def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=Non
         hc, wc = (hin - pi + stride - 1) // stride, (win - pj + stride - 1) // stride
         d = dict(B=dy.B, Hin=dy.t.shape[1], Win=dy.t.shape[2], Ca=dy.Cs, a_stride=1, bf16=1, H=hc, W=wc, Cout=c_n,
                  w_rows=rows_alloc, kchunks=kchunks, groups=groups, res_kind=0, res_Cs=0, act=ACT_NONE, slope=0.0,
-                 y_kind=BF16, y_H=hin, y_W=win, y_Cs=out.Cs, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=stride,
+                 scale=scale, y_kind=BF16, y_H=hin, y_W=win, y_Cs=out.Cs, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=stride,
                  y_sw=stride, y_oh=pi, y_ow=pj)
         backend().tapconv(dy.t, wp, None, None, out.t, d)
     return out
@@ -397,8 +459,9 @@ import os as _os
 WGRAD_BF16_X = _os.environ.get("COCOS_WGRAD_BF16_X", "1") != "0"
 
 
-def conv_wgrad(dy, x, ks, stride=1, padding=0):
-    """Backward-weights: dy NT bf16, x the NT the forward read (fp16, or bf16) -> dW fp32 [Cout, Cin, KS, KS]."""
+def conv_wgrad(dy, x, ks, stride=1, padding=0, scale=None):
+    """Backward-weights: dy NT bf16, x the NT the forward read (fp16, or bf16) -> dW fp32 [Cout, Cin, KS, KS]
+    (times the 1-element tensor `scale` when given: it rides in the copy that fixes the layout)."""
     assert dy.kind == BF16 and dy.pad == 0 and x.kind in (F16, BF16)
     if x.kind == F16 and WGRAD_BF16_X:
         x = as_bf16(x)
@@ -409,7 +472,11 @@ def conv_wgrad(dy, x, ks, stride=1, padding=0):
     d = dict(B=dy.B, H=dy.H, W=dy.W, dy_Cs=dy.Cs, Cout=cout, Hin=x.t.shape[1], Win=x.t.shape[2], Ca=x.Cs,
              a_stride=stride, x_f16=1 if x.kind == F16 else 0, Cin=cin, Cin_s=cin_s, groups=groups)
     backend().tapwgrad(dy.t, x.t, ws, d)
-    return ws[:, :, :cin].view(ks, ks, cout, cin).permute(2, 3, 0, 1).contiguous()
+    view = ws[:, :, :cin].view(ks, ks, cout, cin).permute(2, 3, 0, 1)
+    if scale is None:
+        return view.contiguous()
+    out = torch.empty((cout, cin, ks, ks), dtype=torch.float32, device=ws.device)
+    return torch.mul(view, scale.reshape(()), out=out)
 
 
 def bias_grad(dy):
@@ -440,14 +507,15 @@ def spade_mod_fwd(x, gb, C, pad=0, slope=1.0, eps=1e-5, split_out=False):
     return y, mean, rstd
 
 
-def spade_mod_bwd(dy, x, gb, mean, rstd, C, pad, slope, dx=None):
-    """dy bf16 (halo `pad`) -> (dx bf16 raw-shaped, dgb bf16).  dx given: accumulate into it."""
+def spade_mod_bwd(dy, x, gb, mean, rstd, C, pad, slope, dx=None, gb_W=0):
+    """dy bf16 (halo `pad`) -> (dx bf16 raw-shaped, dgb bf16).  dx given: accumulate into it.  gb_W: gb (and dgb) are in
+    the interleaved channel order of the SPADE-epilogue convolution."""
     assert dy.kind == BF16 and dy.pad == pad
     acc = dx is not None
     if dx is None:
         dx = new(x.B, x.H, x.W, C, BF16, x.t.device)
     dgb = new(x.B, x.H, x.W, 2 * C, BF16, x.t.device)
-    backend().spade_bwd(dy, x, gb, mean, rstd, dx, acc, dgb, C, pad, slope)
+    backend().spade_bwd(dy, x, gb, mean, rstd, dx, acc, dgb, C, pad, slope, gb_W)
     return dx, dgb
 
 

@@ -23,11 +23,12 @@ class Var:
 
 
 class Param:
-    """A weight / bias of the boundary Function (fp32 torch tensor); g accumulates its gradient."""
-    __slots__ = ("t", "g", "need")
+    """A weight / bias of the boundary Function (fp32 torch tensor); g accumulates its gradient.  scale: the Param of
+    the 1-element factor the convolution applies in its epilogue (spectral norm: t = weight_orig, scale = 1/sigma)."""
+    __slots__ = ("t", "g", "need", "scale")
 
     def __init__(self, t, need=True):
-        self.t, self.g, self.need = t, None, need
+        self.t, self.g, self.need, self.scale = t, None, need, None
 
     def add(self, g):
         self.g = g if self.g is None else self.g + g
@@ -129,6 +130,26 @@ def unpack_out(tp, x):
 
 
 # ------------------------------------------------------------------------------------------------ ops
+def _conv_backward(x, W, b, dz, stride, padding, dx_ch):
+    """Backward-weights / bias / backward-data of a tap convolution from dz (bf16, no halo)."""
+    xv, ks = x.v, W.t.shape[2]
+    sc = None if W.scale is None else W.scale.t
+    if W.need:
+        # with an epilogue scale s the layer computed conv(x, s * W): dL/dW = s * G and dL/ds = <G, W>, where
+        # G = dz^T x is what the backward-weights GEMM produces (the s * lands in its layout-fixing copy)
+        gw = nhwc.conv_wgrad(dz, xv, ks, stride=stride, padding=padding, scale=sc)
+        if sc is not None and W.scale.need:
+            W.scale.add((torch.dot(gw.reshape(-1), W.t.reshape(-1)) / sc.reshape(())).reshape(sc.shape))
+        W.add(gw)
+    if b is not None and b.need:
+        b.add(nhwc.bias_grad(dz))
+    if x.need:
+        c_lo, c_n = dx_ch if dx_ch is not None else (0, None)
+        dx = nhwc.conv_dgrad(dz, W.t, (xv.t.shape[1], xv.t.shape[2]), stride=stride, padding=padding,
+                             in_pad=xv.pad, c_lo=c_lo, c_n=c_n, scale=sc)
+        acc(x, dx)
+
+
 def conv(tp, x, W, b=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kind=F16, out_pad=0, split_out=False,
          res=None, dx_ch=None, wsplit=None, nchw=False):
     """nn.Conv2d on the tap-convolution kernels, forward + (recorded) backward-data / backward-weights.
@@ -136,32 +157,25 @@ def conv(tp, x, W, b=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kin
     gradient.  nchw=True: the result is a fp32 NCHW Function output (returned as a torch tensor)."""
     ks = W.t.shape[2]
     xv = x.v
+    sc = None if W.scale is None else W.scale.t
     if nchw:
         h = nhwc.conv_out_size(xv.t.shape[1], ks, padding, stride)
         w = nhwc.conv_out_size(xv.t.shape[2], ks, padding, stride)
         y = torch.empty((xv.B, W.t.shape[0], h, w), dtype=torch.float32, device=xv.t.device)
         nhwc.conv(xv, W.t, None if b is None else b.t, stride=stride, padding=padding, act=act, slope=slope,
-                  nchw_out=y, wsplit=wsplit)
+                  nchw_out=y, wsplit=wsplit, scale=sc)
         out = None
     else:
         y = nhwc.conv(xv, W.t, None if b is None else b.t, stride=stride, padding=padding, act=act, slope=slope,
                       out_kind=out_kind, out_pad=out_pad, split_out=split_out, res=None if res is None else res.v,
-                      wsplit=wsplit)
+                      wsplit=wsplit, scale=sc)
         out = Var(y)
 
     def backward_from(dz):
         """dz: bf16 NT, no halo, gradient of the pre-activation conv output."""
         if res is not None and res.need:
             acc(res, dz)
-        if W.need:
-            W.add(nhwc.conv_wgrad(dz, xv, ks, stride=stride, padding=padding))
-        if b is not None and b.need:
-            b.add(nhwc.bias_grad(dz))
-        if x.need:
-            c_lo, c_n = dx_ch if dx_ch is not None else (0, None)
-            dx = nhwc.conv_dgrad(dz, W.t, (xv.t.shape[1], xv.t.shape[2]), stride=stride, padding=padding,
-                                 in_pad=xv.pad, c_lo=c_lo, c_n=c_n)
-            acc(x, dx)
+        _conv_backward(x, W, b, dz, stride, padding, dx_ch)
 
     if nchw:
         def seed(g):
@@ -201,6 +215,25 @@ def spade(tp, x, gb, C, pad, slope, split):
         if x.need:
             x.g = dx
         acc(gb, dgb)
+    tp.add(bwd)
+    return out
+
+
+def spade_conv(tp, x, actv, W, b, C, pad, slope, split, wsplit=None, gb_kind=F16):
+    """SPADE as ONE convolution launch (nhwc.conv_spade): W / b = mlp_gamma and mlp_beta interleaved, actv the operand
+    relu(mlp_shared(seg)), x the raw activation; the epilogue modulates PONO(x) and writes the next operand."""
+    y, gb, mean, rstd = nhwc.conv_spade(actv.v, W.t, None if b is None else b.t, x.v, C, pad, slope, split_out=split,
+                                        want_gb=tp.record, gb_kind=gb_kind, wsplit=wsplit)
+    out = Var(y)
+    gw = nhwc.spade_interleave(C)
+
+    def bwd():
+        if out.g is None:
+            return
+        dx, dgb = nhwc.spade_mod_bwd(out.g, x.v, gb, mean, rstd, C, pad, slope, dx=x.g if x.need else None, gb_W=gw)
+        if x.need:
+            x.g = dx
+        _conv_backward(actv, W, b, dgb, 1, 0, None)
     tp.add(bwd)
     return out
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define COCOS_ABI_VERSION 3
+#define COCOS_ABI_VERSION 5
 
 int cocos_abi_version(void);
 const char* cocos_last_error(void);
@@ -180,7 +180,9 @@ int cocos_inst_act_bwd(const float* dy, const float* x, const float* mean, const
  * scattered through y_sh/y_sw/y_oh/y_ow).  Reads outside the image or beyond channel Ca are zero.
  *   x   : 16-bit (fp16, or bf16 if `bf16`) NHWC [B, Hin, Win, Ca], Ca % 8 == 0; a_stride 2 needs even Hin, Win.
  *   w   : same 16-bit type, [w_rows >= Cout, ngroups*kchunks*64] (cocos_pack_w), rows >= Cout zero.
- *   epilogue: + bias[n] (fp32, may be NULL), + res[b,h,w,n] (kind 1 or 3, channel stride res_Cs, may be NULL),
+ *   epilogue: * scale[0] (device fp32 scalar, may be NULL: the 1/sigma of a spectrally normalised layer,
+ *             normalization.py:30-31 -- the weights stay un-normalised in w), + bias[n] (fp32, may be NULL),
+ *             + res[b,h,w,n] (kind 1 or 3, channel stride res_Cs, may be NULL),
  *             act 0 none / 1 ReLU / 2 LeakyReLU(slope) / 3 tanh.
  *   y   : kind y_kind.  NHWC kinds: [B, y_H + 2*y_pad, y_W + 2*y_pad, y_Cs], channel offset y_coff; output pixel
  *         (h, w) lands at (h*y_sh + y_oh, w*y_sw + y_ow) (+ y_pad); y_reflect fills the 1-pixel halo by reflection
@@ -192,6 +194,7 @@ typedef struct cocos_tapconv_desc {
   const float* bias;
   const void* res;
   void* y;
+  const float* scale;
   int B, Hin, Win, Ca, a_stride, bf16;
   int H, W, Cout, w_rows;
   int ngroups, kchunks;
@@ -201,6 +204,21 @@ typedef struct cocos_tapconv_desc {
   int res_kind, res_Cs, act;
   float slope;
   int y_kind, y_H, y_W, y_Cs, y_coff, y_lo_off, y_pad, y_reflect, y_sh, y_sw, y_oh, y_ow;
+  /* SPADE modulation epilogue (mod_W = 64 | 128; 0 = off): the convolution is mlp_gamma and mlp_beta at once
+   * (normalization.py:118-120,135-136) with Cout = 2C output rows ordered per N tile as [gamma of mod_W channels |
+   * beta of the same channels], and the epilogue emits the operand of the NEXT convolution directly:
+   *   y[b,h,w,c] = reflect_pad(lrelu(PONO(x)[b,h,w,c] * (1 + gamma) + beta, slope))   (normalization.py:63-68,149;
+   *   architecture.py:73-74,94-95) -- y fp16 [B, H+2*y_pad, W+2*y_pad, y_Cs] with C channels (+ lo terms),
+   *   mod_x the raw activation (kind 1|3, [B,H,W,mod_x_Cs]), mod_mean / mod_rstd its per-pixel PONO statistics
+   *   (cocos_pono_stats_nhwc); gb (optional, kind 1|3, [B,H,W,gb_Cs >= 2C], same interleaved channel order as the
+   *   rows) keeps the raw gamma / beta for cocos_spade_mod_nhwc_bwd.  act must be 2 (LeakyReLU; slope 1 = none). */
+  int mod_W;
+  const void* mod_x;
+  int mod_x_kind, mod_x_Cs;
+  const float* mod_mean;
+  const float* mod_rstd;
+  void* gb;
+  int gb_kind, gb_Cs;
 } cocos_tapconv_desc;
 int cocos_tapconv(const cocos_tapconv_desc* desc, void* stream);
 
@@ -242,9 +260,13 @@ int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb
                              int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
                              float slope, float eps, void* stream);
 int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kind, int x_Cs, const void* gb,
-                             int gb_kind, int gb_Cs, const float* mean, const float* rstd, void* dx, int dx_Cs,
-                             int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad, float slope,
-                             void* stream);
+                             int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx,
+                             int dx_Cs, int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad,
+                             float slope, void* stream);
+/* Per-pixel PONO statistics of x (kind 1|3) [npix, Cs] over its C channels: mean and 1/sqrt(unbiased var + eps)
+ * (normalization.py:63-68), for the SPADE epilogue of cocos_tapconv. */
+int cocos_pono_stats_nhwc(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,
+                          void* stream);
 
 /* InstanceNorm2d(affine=False) statistics over NHWC: stats[b, c] = {sum, sum of squares} over the HW pixels
  * (generator.py:104-113, discriminator.py:92-115, correspondence.py:19,23 with normalization.py:52-53). */

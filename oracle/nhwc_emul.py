@@ -72,8 +72,12 @@ class EmulBackend:
             xg = self._gather(xf, s, g, H, W, kc)
             assert torch.isfinite(xg).all(), "tapconv reads uninitialised / non-finite activations"
             acc += xg @ wf[:Cout, gi * kc:(gi + 1) * kc].t()
+        if d.get("scale") is not None:
+            acc = acc * d["scale"].float().reshape(())
         if bias is not None:
             acc = acc + bias.float()
+        if d.get("mod") is not None:
+            return self._spade_epilogue(acc, y, d)
         if res is not None:
             acc = acc + res.float()[..., :Cout]
         act = d["act"]
@@ -102,6 +106,29 @@ class EmulBackend:
                 if d["y_lo_off"]:
                     lo = (acc - hi)[:, rm][:, :, cm]
                     y[:, rt[rm][:, None], ct[cm][None, :], co + d["y_lo_off"]:co + d["y_lo_off"] + Cout] = lo.to(y.dtype)
+
+    def _spade_epilogue(self, acc, y, d):
+        """acc [B,H,W,2C] in the interleaved order -> y = reflect_pad(lrelu(PONO(x)(1 + gamma) + beta)); gb raw."""
+        mod = d["mod"]
+        W, C = mod["W"], d["Cout"] // 2
+        a = acc.reshape(acc.shape[:3] + (C // W, 2, W))
+        gamma, beta = a[..., 0, :].reshape(acc.shape[:3] + (C,)), a[..., 1, :].reshape(acc.shape[:3] + (C,))
+        if mod["gb"] is not None:
+            mod["gb"].t[..., :2 * C] = self._round(acc, mod["gb"].kind).to(mod["gb"].t.dtype)
+        xf = mod["x"].t.float()[..., :C]
+        z = (xf - mod["mean"][..., None]) * mod["rstd"][..., None] * (1 + gamma) + beta
+        z = torch.where(z > 0, z, z * d["slope"])
+        p, hi = d["y_pad"], None
+        hi = self._round(z, F16)
+        y[..., :C] = self._pad_reflect(hi, p).to(y.dtype)
+        if d["y_lo_off"]:
+            y[..., d["y_lo_off"]:d["y_lo_off"] + C] = self._pad_reflect(z - hi, p).to(y.dtype)
+
+    def pono_stats(self, x, C, eps, mean, rstd):
+        xf = x.t.float()[..., :C]
+        m = xf.mean(3, keepdim=True)
+        mean.copy_(m[..., 0])
+        rstd.copy_((xf.var(3, keepdim=True, unbiased=True) + eps).rsqrt()[..., 0])
 
     def tapwgrad(self, dy, x, ws, d):
         s, H, W = d["a_stride"], d["H"], d["W"]
@@ -171,15 +198,22 @@ class EmulBackend:
         rstd.copy_(r[..., 0])
         self._write_op(y, z)
 
-    def spade_bwd(self, dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope):
+    def spade_bwd(self, dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope, gb_W=0):
         d = self._fold(dy.t.float()[..., :C], pad)
-        xf, g = x.t.float()[..., :C], gb.t.float()
+        xf, g = x.t.float()[..., :C], gb.t.float()[..., :2 * C]
+        if gb_W:  # interleaved [gamma of W | beta of W] per 2W channels -> canonical [gamma | beta]
+            gi = g.reshape(g.shape[:3] + (C // gb_W, 2, gb_W))
+            g = torch.cat((gi[..., 0, :].reshape(g.shape[:3] + (C,)), gi[..., 1, :].reshape(g.shape[:3] + (C,))), 3)
         m, r = mean[..., None], rstd[..., None]
         xh = (xf - m) * r
         z = xh * (1 + g[..., :C]) + g[..., C:2 * C]
         d = torch.where(z > 0, d, d * slope)
-        dgb.t[..., :C] = (d * xh).to(dgb.t.dtype)
-        dgb.t[..., C:2 * C] = d.to(dgb.t.dtype)
+        if gb_W:
+            both = torch.stack(((d * xh).reshape(d.shape[:3] + (C // gb_W, gb_W)), d.reshape(d.shape[:3] + (C // gb_W, gb_W))), 4)
+            dgb.t[..., :2 * C] = both.reshape(d.shape[:3] + (2 * C,)).to(dgb.t.dtype)
+        else:
+            dgb.t[..., :C] = (d * xh).to(dgb.t.dtype)
+            dgb.t[..., C:2 * C] = d.to(dgb.t.dtype)
         e = d * (1 + g[..., :C])
         m1 = e.sum(3, keepdim=True) / C
         m2 = (e * xh).sum(3, keepdim=True) / (C - 1)

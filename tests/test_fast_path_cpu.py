@@ -25,7 +25,7 @@ class CountingEmul(EmulBackend):
     def __init__(self):
         super().__init__(exact=True)
         self.calls = {"tapconv": 0, "tapwgrad": 0, "spade_fwd": 0, "inst_fwd": 0, "maxpool_fwd": 0, "maxpool_bwd": 0,
-                      "stride2": 0}
+                      "stride2": 0, "spade_epilogue": 0}
 
     def maxpool_fwd(self, *a, **k):
         self.calls["maxpool_fwd"] += 1
@@ -38,6 +38,7 @@ class CountingEmul(EmulBackend):
     def tapconv(self, *a, **k):
         self.calls["tapconv"] += 1
         self.calls["stride2"] += int(a[5]["a_stride"] == 2 and len(a[5]["groups"]) == 16)  # PatchGAN 4x4 / stride 2
+        self.calls["spade_epilogue"] += int(a[5].get("mod") is not None)  # SPADE modulation in the conv epilogue
         return super().tapconv(*a, **k)
 
     def tapwgrad(self, *a, **k):
@@ -76,7 +77,9 @@ def test_ade20k_train_step_on_the_tape_matches_reference_golden():
     finally:
         nhwc.set_backend(old)
     # the networks really ran on the tape: 3 adaptor passes x (5 + 24) convs, 7 generator blocks, the residual stack ...
-    assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_fwd"] > 30, be.calls
+    # every SPADE layer modulates in the epilogue of its gamma|beta convolution (no separate modulation pass)
+    assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_epilogue"] > 30 \
+        and be.calls["spade_fwd"] == 0, be.calls
     # ... the VGG19 feature net (3 forward passes x 4 poolings, one backward) and both PatchGANs (3 stride-2 4x4
     # convolutions each, G step: fake + real halves, D step: one batch)
     assert be.calls["maxpool_fwd"] == 12 and be.calls["maxpool_bwd"] == 4 and be.calls["stride2"] >= 18, be.calls

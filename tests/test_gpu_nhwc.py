@@ -269,3 +269,50 @@ def test_maxpool2_nhwc(B, C, H, W):
     yr.backward(dy.bfloat16().float())
     assert torch.equal(want[0].float().permute(0, 3, 1, 2), yr.detach())
     assert torch.equal(want[1].float().permute(0, 3, 1, 2), xr.grad)
+
+
+@pytest.mark.parametrize("C,H,W,B,pad,xk,split", [(128, 64, 64, 2, 1, nhwc.F16, False), (512, 32, 32, 2, 1, nhwc.F32, True),
+                                                   (64, 64, 64, 2, 1, nhwc.F16, False), (1024, 8, 8, 4, 0, nhwc.F16, False)])
+def test_conv_spade_epilogue(C, H, W, B, pad, xk, split):
+    """SPADE as one convolution launch: gamma|beta conv + PONO + modulation + LeakyReLU + reflection halo in the
+    epilogue (cocos_tapconv with mod_W, cocos_pono_stats_nhwc), and its backward through the interleaved gb layout
+    (cocos_spade_mod_nhwc_bwd with gb_W), against the emulation of the same entry points."""
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    actv = torch.randn(B, 128, H, W, generator=g).relu()
+    wg, wb = torch.randn(C, 128, 3, 3, generator=g) * 0.03, torch.randn(C, 128, 3, 3, generator=g) * 0.03
+    bg, bb = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    dy = torch.randn(B, C, H + 2 * pad, W + 2 * pad, generator=g)
+    Wd = nhwc.spade_interleave(C)
+    assert Wd
+
+    def fn(dev):
+        xr = nhwc.pack(x.to(dev), xk)
+        a = nhwc.pack(actv.to(dev), nhwc.F16, pad=1, split=split)
+        w = nhwc.interleave_rows(wg.to(dev), wb.to(dev), Wd)
+        b = nhwc.interleave_rows(bg.to(dev), bb.to(dev), Wd)
+        y, gb, mean, rstd = nhwc.conv_spade(a, w, b, xr, C, pad, 0.2, split_out=split, want_gb=True, gb_kind=xk)
+        dyn = nhwc.pack(dy.to(dev), nhwc.BF16)
+        dyn = nhwc.NT(dyn.t, nhwc.BF16, C, pad)  # the same buffer seen as a haloed gradient
+        dx, dgb = nhwc.spade_mod_bwd(dyn, xr, gb, mean, rstd, C, pad, 0.2, gb_W=Wd)
+        return y.t, gb.t, mean, rstd, dx.t, dgb.t
+
+    got, want = both(fn)
+    assert rel(got[2], want[2]) < 1e-5 and rel(got[3], want[3]) < 1e-4
+    assert rel(got[1], want[1]) < 2e-3          # raw gamma | beta
+    assert rel(got[0], want[0]) < 3e-3          # the operand (hi [+ lo]) incl. halo
+    assert rel(got[4], want[4]) < 1e-2 and rel(got[5], want[5]) < 1e-2
+    # and the emulation of the fused layer is the unfused reference expression
+    xf, gamma, beta = x, F_conv(actv, wg, bg), F_conv(actv, wb, bb)
+    m = xf.mean(1, keepdim=True)
+    z = (xf - m) / (xf.var(1, keepdim=True) + 1e-5).sqrt() * (1 + gamma) + beta
+    z = torch.nn.functional.leaky_relu(z, 0.2)
+    if pad:
+        z = torch.nn.functional.pad(z, (pad,) * 4, mode="reflect")
+    ref = z.permute(0, 2, 3, 1)
+    assert rel(want[0].float()[..., :C] + (want[0].float()[..., want[0].shape[3] // 2:][..., :C] if split else 0), ref) < 3e-3
+
+
+def F_conv(actv, w, b):
+    a = torch.nn.functional.pad(actv.half().float(), (1, 1, 1, 1), mode="reflect")
+    return torch.nn.functional.conv2d(a, w.half().float(), b)
