@@ -23,8 +23,7 @@ SIGNATURES = {
     "cocos_spade_mod_fwd": [_vp] * 5 + [_c_int] * 5 + [_c_float, _c_float, _c_int, _vp],
     "cocos_spade_mod_bwd": [_vp] * 7 + [_c_int] * 5 + [_c_float, _c_int, _vp],
     "cocos_cast_pitch": [_vp, _vp, ctypes.c_longlong] + [_c_int] * 6 + [_vp],
-    "cocos_conv_wgrad": [_vp, _vp, _vp] + [_c_int] * 12 + [_vp],
-    "cocos_cast_taps": [_vp, _vp, ctypes.c_longlong] + [_c_int] * 7 + [_vp],
+    "cocos_conv_wgrad": [_vp, _vp, _vp] + [_c_int] * 11 + [_vp],
     "cocos_conv_fwd": [_vp, _vp, _vp, _vp] + [_c_int] * 10 + [_vp],
     "cocos_normalize_pack": [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _vp],
     "cocos_normalize_pack_bwd": [_vp] * 7 + [_c_int] * 5 + [_vp],

@@ -129,22 +129,13 @@ int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int W
   return cast_pitch_launch(src, dst, rows, Win, Wout, Wp, nshift, off, bf16, static_cast<cudaStream_t>(stream));
 }
 
-int cocos_cast_taps(const float* src, void* dst, long long rows, int Hin, int Win, int H, int W, int KS, int off,
-                    int bf16, void* stream) {
-  if (!src || !dst) {
-    set_error("cast_taps: null pointer");
-    return -1;
-  }
-  return cast_taps_launch(src, dst, rows, Hin, Win, H, W, KS, off, bf16, static_cast<cudaStream_t>(stream));
-}
-
 int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
-                     int KS, int off, int dy_bf16, int x_bf16, int flat, void* stream) {
+                     int KS, int off, int dy_bf16, int x_bf16, void* stream) {
   if (!dy || !x || !ws) {
     set_error("conv_wgrad: null pointer");
     return -1;
   }
-  return conv_wgrad_launch(dy, x, ws, B, H, W, Hin, Win, Cout, Cin, KS, off, dy_bf16, x_bf16, flat,
+  return conv_wgrad_launch(dy, x, ws, B, H, W, Hin, Win, Cout, Cin, KS, off, dy_bf16, x_bf16,
                            static_cast<cudaStream_t>(stream));
 }
 

@@ -38,7 +38,6 @@ struct WgradParams {
   int bw, bh, chunks_w, chunks_h;  // a K chunk = bh rows x bw columns = 64 pixels
   int total_chunks, chunks_per_split, splits;
   int a_bf16, b_bf16;
-  int flat;  // x = KS*KS fully shifted copies over flattened pixels (narrow maps): no row shift in the coordinate
   int dbg;  // COCOS_WG_DBG bring-up knock-outs: 1 no x load, 2 no dy load, 4 no MMA, 8 no stores
   float* ws;  // [KS*KS, Cin, Cout]
 };
@@ -112,8 +111,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         mbar_expect_tx(full, ((p.dbg & 2) ? 0 : ATOM_BYTES) + ((p.dbg & 1) ? 0 : (BN / 128) * ATOM_BYTES));
         const int w0 = cw * p.bw, h0 = ch * p.bh;
         if (!(p.dbg & 2)) tma_load_4d(smem0 + st * STAGE_BYTES, &tm_dy, full, w0, h0, n0, b);
-        if (!(p.dbg & 1)) tma_load_4d(smem0 + st * STAGE_BYTES + ATOM_BYTES, &tm_x, full, w0, p.flat ? 0 : h0 + r - p.off, c0,
-                                        (p.flat ? tap : s) * p.B + b);
+        if (!(p.dbg & 1)) tma_load_4d(smem0 + st * STAGE_BYTES + ATOM_BYTES, &tm_x, full, w0, h0 + r - p.off, c0, s * p.B + b);
         if (++st == STAGES) { st = 0; ph ^= 1; }
         if (++cw == p.chunks_w) {
           cw = 0;
@@ -202,53 +200,7 @@ cast_pitch_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, lon
   }
 }
 
-// fp32 [rows, Hin, Win] -> 16-bit [KS*KS, rows, HWp]: copy (r,s) holds dst[p = h*W + w] = src[h + r - off][w + s - off]
-// (zero outside the image) for the H*W output pixels, flattened: the operand layout of K2w's flat mode (maps narrower
-// than 64, where a row of the image is shorter than one 128-byte K chunk).
-__global__ void __launch_bounds__(256)
-cast_taps_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int Hin, int Win, int H,
-                 int W, int HWp, int KS, int off, int bf16) {
-  const int HW = H * W;
-  const int pq = (HW + 3) >> 2;
-  const long long total = rows * pq;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
-    const long long row = i / pq;
-    const int p0 = static_cast<int>(i - row * pq) * 4;
-    const float* sp = src + row * Hin * Win;
-    for (int tap = 0; tap < KS * KS; ++tap) {
-      const int r = tap / KS, s = tap - r * KS;
-      uint16_t o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = p0 + j;
-        const int h = p / W, w = p - h * W;
-        const int hh = h + r - off, ww = w + s - off;
-        const float x = (p < HW && hh >= 0 && hh < Hin && ww >= 0 && ww < Win) ? __ldg(sp + hh * Win + ww) : 0.f;
-        o[j] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(x)) : __half_as_ushort(__float2half_rn(x));
-      }
-      *reinterpret_cast<uint2*>(dst + (static_cast<long long>(tap) * rows + row) * HWp + p0) =
-          make_uint2(o[0] | (uint32_t(o[1]) << 16), o[2] | (uint32_t(o[3]) << 16));
-    }
-  }
-}
-
 }  // namespace
-
-int cast_taps_launch(const float* src, void* dst, long long rows, int Hin, int Win, int H, int W, int KS, int off,
-                     int bf16, cudaStream_t stream) {
-  if (rows <= 0 || Hin <= 0 || Win <= 0 || H <= 0 || W <= 0 || (KS != 1 && KS != 3) || off < 0 || off >= KS) {
-    set_error("cast_taps: bad shape (rows=%lld Hin=%d Win=%d H=%d W=%d KS=%d off=%d)", rows, Hin, Win, H, W, KS, off);
-    return -1;
-  }
-  const int HWp = (H * W + 7) / 8 * 8;
-  const long long total = rows * ((H * W + 3) / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  cast_taps_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), rows, Hin, Win, H, W,
-                                                                 HWp, KS, off, bf16);
-  COCOS_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
 
 int cast_pitch_launch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,
                       int bf16, cudaStream_t stream) {
@@ -266,26 +218,21 @@ int cast_pitch_launch(const float* src, void* dst, long long rows, int Win, int 
 }
 
 int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
-                      int KS, int off, int a_bf16, int b_bf16, int flat, cudaStream_t stream) {
+                      int KS, int off, int a_bf16, int b_bf16, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || W <= 0 || Hin <= 0 || Win <= 0 || Cout <= 0 || Cin <= 0 || (KS != 1 && KS != 3) || off < 0 ||
       off >= KS) {
     set_error("conv_wgrad: bad shape (B=%d H=%d W=%d Hin=%d Win=%d Cout=%d Cin=%d KS=%d off=%d)", B, H, W, Hin, Win,
               Cout, Cin, KS, off);
     return -1;
   }
-  if (flat) {  // flattened pixels: one "row" of H*W pixels per (image, channel); both shifts live in the x copies
-    W = H * W;
-    H = 1;
-    Hin = 1;
-  }
   WgradParams p;
-  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Cin = Cin; p.KS = KS; p.off = off; p.flat = flat ? 1 : 0;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Cin = Cin; p.KS = KS; p.off = off;
   int bw = 8;
   while (bw < W && bw < 64) bw *= 2;
   if (bw < 64) {
     // a {bw < 64, bh, C, 1} box does not land as dense 128-byte swizzled rows (measured: illegal address on B200), so
     // narrow layers are not taken here; the host routes them to the library wgrad.
-    set_error("conv_wgrad: %s=%d < 64 is not supported", flat ? "H*W" : "W", W);
+    set_error("conv_wgrad: W=%d < 64 is not supported", W);
     return -1;
   }
   p.bw = bw; p.bh = 64 / bw;
@@ -322,8 +269,7 @@ int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, in
   {
     // x arrives as KS column-shifted copies [KS][B][Cin][Hin][Wp] (copy s starts at column s - off), because a TMA
     // box must start on a 16-byte boundary of the innermost dimension: the tap's column shift cannot be a coordinate.
-    // (flat mode: KS*KS copies with both shifts baked in, [KS*KS][B][Cin][HWp])
-    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Hin, (uint64_t)Cin, (uint64_t)B * (flat ? KS * KS : KS)};
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)Hin, (uint64_t)Cin, (uint64_t)B * KS};
     const uint64_t pitches[3] = {(uint64_t)Wp * 2, (uint64_t)Hin * Wp * 2, (uint64_t)Cin * Hin * Wp * 2};
     const uint32_t box[4] = {(uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)(BN > 256 ? 256 : BN), 1};
     if ((rc = make_tmap_f16_4d(&tm_x, x, dims, pitches, box))) return rc;

@@ -40,10 +40,8 @@ int pack_v_f16_launch(const float* src, void* dst, int B, int Cv, int Nk, int Cv
 
 int cast_pitch_launch(const float* src, void* dst, long long rows, int Win, int Wout, int Wp, int nshift, int off,
                       int bf16, cudaStream_t stream);
-int cast_taps_launch(const float* src, void* dst, long long rows, int Hin, int Win, int H, int W, int KS, int off,
-                     int bf16, cudaStream_t stream);
 int conv_wgrad_launch(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
-                      int KS, int off, int a_bf16, int b_bf16, int flat, cudaStream_t stream);
+                      int KS, int off, int a_bf16, int b_bf16, cudaStream_t stream);
 int conv_fwd_launch(const void* x, const void* wt, const float* bias, float* y, int B, int H, int W, int Hin, int Win,
                     int Cp, int Cout, int KS, int off, int bf16, cudaStream_t stream);
 

@@ -330,42 +330,23 @@ def cast_pitch(x, bf16, wout=None, nshift=1, off=0):
 WGRAD_X_BF16 = _os.environ.get("COCOS_WGRAD_X_BF16", "1") == "1"  # mixed bf16 x fp16 operands are an illegal instruction
 
 
-def cast_taps(x, h, w, ks, off, bf16):
-    """fp32 [B,C,Hin,Win] -> 16-bit [KS*KS, B, C, HWp]: the fully shifted, pixel-flattened copies of K2w's flat mode."""
-    x = x.contiguous()
-    _req(x, torch.float32, "x")
-    b, c, hin, win = x.shape
-    out = torch.empty((ks * ks, b, c, round_up(h * w, 8)), dtype=torch.bfloat16 if bf16 else torch.float16,
-                      device=x.device)
-    _lib.check(_lib.lib().cocos_cast_taps(x.data_ptr(), out.data_ptr(), b * c, hin, win, h, w, ks, off, int(bf16),
-                                          _stream()), "cocos_cast_taps")
-    return out
-
-
-def conv_wgrad_native(dy, x, ks, pre_padded, flat=False):
-    """K2w backward-weights: dW [Cout,Cin,KS,KS] = sum over pixels of dy x shifted x (bf16 operands, fp32 accumulate)
-    on the split-K tcgen05 kernel.  dy [B,Cout,H,W], x [B,Cin,Hin,Win] fp32 NCHW.  `flat` (experimental): the
-    pixel-flattened operand layout for maps narrower than 64."""
+def conv_wgrad_native(dy, x, ks, pre_padded):
+    """K2w backward-weights (NCHW operands, the fallback path of layers that are not on the NHWC tape): dW
+    [Cout,Cin,KS,KS] = sum over pixels of dy x shifted x (bf16 operands, fp32 accumulate) on the split-K tcgen05 kernel.
+    dy [B,Cout,H,W], x [B,Cin,Hin,Win] fp32 NCHW, W >= 64."""
     b, cout, h, w = dy.shape
     _, cin, hin, win = x.shape
     off = 0 if pre_padded else ks // 2
-    if flat:
-        dy16 = cast_pitch(dy.contiguous().view(b, cout, h * w), True)
-        x16 = cast_taps(x, h, w, ks, off, WGRAD_X_BF16)
-    else:
-        dy16 = cast_pitch(dy, True)
-        x16 = cast_pitch(x, WGRAD_X_BF16, wout=w, nshift=ks, off=off)
+    dy16 = cast_pitch(dy, True)
+    x16 = cast_pitch(x, WGRAD_X_BF16, wout=w, nshift=ks, off=off)
     ws = torch.empty((ks * ks, cin, cout), dtype=torch.float32, device=dy.device)
     _lib.check(_lib.lib().cocos_conv_wgrad(dy16.data_ptr(), x16.data_ptr(), ws.data_ptr(), b, h, w, hin, win, cout, cin,
-                                           ks, off, 1, int(WGRAD_X_BF16), int(bool(flat)), _stream()),
+                                           ks, off, 1, int(WGRAD_X_BF16), _stream()),
                "cocos_conv_wgrad")
     return ws.view(ks, ks, cin, cout).permute(3, 2, 0, 1).contiguous()
 
 
 NATIVE_WGRAD = _os.environ.get("COCOS_NATIVE_WGRAD", "1") == "1"
-# maps narrower than 64 through K2w's pixel-flattened operand layout: written after the round's GPU budget was spent,
-# so it is opt-in until tests/test_gpu_corr.py::test_conv_wgrad_flat_mode has run on a B200
-WGRAD_NARROW = _os.environ.get("COCOS_WGRAD_NARROW", "0") == "1"
 # backward-data on K2 costs one more transpose-pack + weight re-layout per layer: measured on the eager ade20k step
 # (launch-bound, profiles/README.md) 179 ms with it vs 170.5 ms without, although the GPU-busy time is lower with it
 # (160 vs 163 ms) -- so Pix2PixTrainer turns it on exactly when the iteration is replayed from a CUDA graph.
@@ -393,10 +374,8 @@ class _ConvNative(torch.autograd.Function):
         if need_x and NATIVE_DGRAD:
             dx = conv_dgrad_native(dy, weight, ctx.pre_padded)
             need_x = False
-        wide = dy.shape[3] >= 64
-        narrow_ok = WGRAD_NARROW and dy.shape[2] * dy.shape[3] >= 64
-        if need_w and NATIVE_WGRAD and x.shape[1] >= 128 and (wide or narrow_ok):  # K2w takes the wide layers
-            dw = conv_wgrad_native(dy, x, weight.shape[2], ctx.pre_padded, flat=not wide)
+        if need_w and NATIVE_WGRAD and x.shape[1] >= 128 and dy.shape[3] >= 64:  # K2w takes the wide layers
+            dw = conv_wgrad_native(dy, x, weight.shape[2], ctx.pre_padded)
             if need_b:
                 db = dy.sum((0, 2, 3))
             need_w = need_b = False

@@ -126,16 +126,7 @@ int cocos_cast_pitch(const float* src, void* dst, long long rows, int Win, int W
  * (dy_bf16 = x_bf16 = 1): a bf16 x fp16 instruction descriptor is rejected by the hardware.
  * ws : fp32 [KS*KS, Cin, Cout], fully overwritten (zeroed + atomically accumulated when the pixel range is split). */
 int cocos_conv_wgrad(const void* dy, const void* x, float* ws, int B, int H, int W, int Hin, int Win, int Cout, int Cin,
-                     int KS, int off, int dy_bf16, int x_bf16, int flat, void* stream);
-
-/* Operand copies for the flat mode of cocos_conv_wgrad (`flat` = 1; EXPERIMENTAL, not yet validated on hardware --
- * the host mirror only uses it with COCOS_WGRAD_NARROW=1): for maps narrower than 64 the pixels of one (image, channel)
- * plane are flattened to H*W and BOTH shifts of a tap are baked into KS*KS copies:
- *   dst[(r*KS + s), row, h*W + w] = src[row, h + r - off, w + s - off]   (zero outside [0,Hin)x[0,Win)),
- * 16-bit, pitch H*W rounded up to 8.  dy is then passed as [B, Cout, HWp] (cocos_cast_pitch of the flattened view);
- * H*W >= 64 is required. */
-int cocos_cast_taps(const float* src, void* dst, long long rows, int Hin, int Win, int H, int W, int KS, int off,
-                    int bf16, void* stream);
+                     int KS, int off, int dy_bf16, int x_bf16, void* stream);
 
 /* Fused operand prologue for `--PONO_C` (correspondence.py:273-281 / 283-289): x fp32 [B,C,h,w] (output of the theta
  * or phi 1x1 conv) -> unfold(match_kernel, zero pad) -> minus the mean over K = C*mk*mk -> / (L2 norm over K + eps)

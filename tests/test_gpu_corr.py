@@ -428,25 +428,6 @@ def test_conv_wgrad_native_direct(b, cin, cout, h, w, ks, pre_padded):
     assert _rel(dw.cpu().numpy(), wr.grad.cpu().numpy()) < 4e-3
 
 
-@pytest.mark.skipif(os.environ.get("COCOS_WGRAD_NARROW", "0") != "1",
-                    reason="K2w flat mode is experimental: set COCOS_WGRAD_NARROW=1 (first hardware run pending)")
-@pytest.mark.parametrize("b,cin,cout,h,w,ks,pre_padded", [(2, 128, 256, 16, 16, 3, True), (8, 1024, 128, 8, 8, 3, True),
-                                                         (2, 130, 64, 20, 12, 3, False), (1, 256, 256, 32, 32, 1, False)])
-def test_conv_wgrad_flat_mode(b, cin, cout, h, w, ks, pre_padded):
-    """K2w for maps narrower than 64: pixel-flattened operands, KS*KS fully shifted x copies (cocos_cast_taps)."""
-    import torch.nn.functional as F
-    from cocosnet_b200 import ops
-    g = torch.Generator(device="cuda").manual_seed(cin + w)
-    pad = ks // 2
-    hin, win = (h + 2 * pad, w + 2 * pad) if pre_padded else (h, w)
-    x = torch.randn(b, cin, hin, win, device="cuda", generator=g)
-    dy = torch.randn(b, cout, h, w, device="cuda", generator=g)
-    dw = ops.conv_wgrad_native(dy, x, ks, pre_padded, flat=True)
-    wr = torch.zeros(cout, cin, ks, ks, device="cuda", dtype=torch.float64, requires_grad=True)
-    F.conv2d(x.double(), wr, None, padding=0 if pre_padded else pad).backward(dy.double())
-    assert _rel(dw.cpu().numpy(), wr.grad.cpu().numpy()) < 4e-3
-
-
 def test_conv_wgrad_rejects_narrow_layers():
     from cocosnet_b200 import _lib, ops
     x = torch.randn(1, 64, 18, 18, device="cuda")
