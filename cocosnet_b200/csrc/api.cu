@@ -175,6 +175,12 @@ int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb
                                    slope, eps, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_sn_power_iter(const void* table, int n, int blocks_a, int blocks_b, float* scratch, float* inv_sigma,
+                        float* snapshot, float eps, int training, void* stream) {
+  return sn_power_iter_launch(table, n, blocks_a, blocks_b, scratch, inv_sigma, snapshot, eps, training,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int cocos_pono_stats_nhwc(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,
                           void* stream) {
   if (!x || !mean || !rstd) {

@@ -23,46 +23,47 @@ from ..nhwc import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, F16, F32
 from torch.nn.utils.spectral_norm import SpectralNorm as _SpectralNorm  # noqa: E402
 
 
-def _sn_weight_and_scale(m, hook):
-    """What torch.nn.utils.spectral_norm's pre-forward hook does (one power iteration on the persistent u / v in
-    training mode, sigma = u^T W v with u, v constant; normalization.py:30-31 wraps every generator / discriminator
-    conv with it) -- except for the last line, `weight = weight_orig / sigma`: returns (weight_orig, 1 / sigma)."""
-    weight = getattr(m, hook.name + "_orig")
-    u, v = getattr(m, hook.name + "_u"), getattr(m, hook.name + "_v")
-    wm = weight.reshape(weight.shape[0], -1)
-    if m.training:
-        with torch.no_grad():
-            for _ in range(hook.n_power_iterations):
-                v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=hook.eps, out=v)
-                u = F.normalize(torch.mv(wm, v), dim=0, eps=hook.eps, out=u)
-            if hook.n_power_iterations > 0:
-                u, v = u.clone(memory_format=torch.contiguous_format), v.clone(memory_format=torch.contiguous_format)
-    sigma = torch.dot(u, torch.mv(wm, v))
-    return weight, (1.0 / sigma).reshape(1)
-
-
 class ParamSet:
-    """The tensors that become inputs of the boundary Function (conv weights after their spectral-norm / equal-lr
-    pre-hooks ran -- exactly once per module per forward, like nn.Module.__call__ would) and their Params inside."""
+    """The tensors that become inputs of the boundary Function (conv weights after their equal-lr pre-hooks ran --
+    exactly once per module per forward, like nn.Module.__call__ would) and their Params inside.  Spectrally
+    normalised convolutions (normalization.py:30-31) contribute weight_orig and a 1 / sigma scalar instead of
+    weight_orig / sigma: all layers registered here share ONE multi-layer power-iteration launch sequence
+    (nhwc.backend().sn_power_iter, run when `tensors` is first read), the convolution kernels apply 1 / sigma in their
+    epilogues and the backward adds the rank-1 term of d sigma / d weight."""
 
     def __init__(self):
-        self.tensors, self.slot, self.params = [], {}, None
+        self._tensors, self.slot, self.params = [], {}, None
+        self._sn, self._sn_vec = [], {}
 
     def _add(self, key, t):
         if key not in self.slot:
-            self.slot[key] = len(self.tensors)
-            self.tensors.append(t)
+            self.slot[key] = len(self._tensors)
+            self._tensors.append(t)
+
+    @property
+    def tensors(self):
+        if self._sn:
+            pending, self._sn = self._sn, []
+            training = pending[0][1].training
+            assert all(m.training == training for _, m, _ in pending)
+            entries = [(getattr(m, h.name + "_orig"), getattr(m, h.name + "_u"), getattr(m, h.name + "_v"))
+                       for _, m, h in pending]
+            with torch.no_grad():
+                inv, shot, offs = nhwc.backend().sn_power_iter(entries, training, pending[0][2].eps)
+            for i, (key, m, h) in enumerate(pending):
+                off, r, c = offs[i]
+                self._add(("s", key), inv[i:i + 1])
+                self._sn_vec[key] = (shot[off:off + r], shot[off + r:off + r + c])
+        return self._tensors
 
     def conv(self, m):
         if ("w", id(m)) in self.slot:
             return
         sn = [h for h in m._forward_pre_hooks.values() if isinstance(h, _SpectralNorm)]
-        if len(sn) == 1 and len(m._forward_pre_hooks) == 1 and sn[0].dim == 0 and sn[0].name == "weight":
-            # spectral norm without ever forming weight_orig / sigma: the convolution kernels multiply their
-            # accumulators by 1/sigma (one scalar), the weight the tape packs and differentiates is weight_orig
-            w, inv_sigma = _sn_weight_and_scale(m, sn[0])
-            self._add(("w", id(m)), w)
-            self._add(("s", id(m)), inv_sigma)
+        if len(sn) == 1 and len(m._forward_pre_hooks) == 1 and sn[0].dim == 0 and sn[0].name == "weight" \
+                and sn[0].n_power_iterations == 1:
+            self._add(("w", id(m)), getattr(m, "weight_orig"))
+            self._sn.append((id(m), m, sn[0]))
         else:
             for hook in m._forward_pre_hooks.values():
                 hook(m, (None,))
@@ -91,7 +92,8 @@ class ParamSet:
         self.params = params
         for (kind, key), i in self.slot.items():
             if kind == "s":
-                params[self.slot[("w", key)]].scale = params[i]
+                w = params[self.slot[("w", key)]]
+                w.scale, w.sn = params[i], self._sn_vec[key]
 
     def w(self, m):
         return self.params[self.slot[("w", id(m))]]

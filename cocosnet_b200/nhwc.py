@@ -188,6 +188,38 @@ class NativeBackend:
                                                      x.B, C, x.H, x.W, pad, float(slope), float(eps), _stream()),
                    "cocos_spade_mod_nhwc_fwd")
 
+    _sn_tables = {}
+
+    def sn_power_iter(self, entries, training, eps):
+        """entries: [(weight_orig [rows, ...], u [rows], v [cols])] -> (inv_sigma [n], snapshot flat, offsets): one
+        power iteration on all layers in three launches (cocos_sn_power_iter); u, v are updated in place when training.
+        The device table is built once per set of layers (the parameter / buffer addresses never change)."""
+        dev = entries[0][0].device
+        key = tuple((w.data_ptr(), u.data_ptr(), v.data_ptr(), w.shape[0], w.numel() // w.shape[0]) for w, u, v in entries)
+        tab = NativeBackend._sn_tables.get(key)
+        if tab is None:
+            rows, ba, bb, snap = [], 0, 0, 0
+            offs = []
+            for w, u, v in entries:
+                r, c = w.shape[0], w.numel() // w.shape[0]
+                assert w.is_contiguous() and u.numel() == r and v.numel() == c and w.dtype == torch.float32
+                rows.append([w.data_ptr(), u.data_ptr(), v.data_ptr(), r, c, ba, bb, snap])
+                offs.append((snap, r, c))
+                ba += (c + 127) // 128
+                bb += (r + 7) // 8
+                snap += r + c
+            table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            tab = NativeBackend._sn_tables[key] = (table, ba, bb, snap, offs)
+        table, ba, bb, snap, offs = tab
+        n = len(entries)
+        scratch = torch.empty((2 * n,), dtype=torch.float32, device=dev)
+        inv = torch.empty((n,), dtype=torch.float32, device=dev)
+        shot = torch.empty((snap,), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.cocos_sn_power_iter(table.data_ptr(), n, ba, bb, scratch.data_ptr(), inv.data_ptr(),
+                                                shot.data_ptr(), float(eps), int(bool(training)), _stream()),
+                   "cocos_sn_power_iter", kernels=3 if training else 2)
+        return inv, shot, offs
+
     def pono_stats(self, x, C, eps, mean, rstd):
         _lib.check(self.lib.cocos_pono_stats_nhwc(x.t.data_ptr(), x.kind, x.Cs, C, x.t.numel() // x.Cs, float(eps),
                                                   mean.data_ptr(), rstd.data_ptr(), _stream()), "cocos_pono_stats_nhwc")

@@ -25,10 +25,11 @@ class Var:
 class Param:
     """A weight / bias of the boundary Function (fp32 torch tensor); g accumulates its gradient.  scale: the Param of
     the 1-element factor the convolution applies in its epilogue (spectral norm: t = weight_orig, scale = 1/sigma)."""
-    __slots__ = ("t", "g", "need", "scale")
+    __slots__ = ("t", "g", "need", "scale", "sn")
 
     def __init__(self, t, need=True):
         self.t, self.g, self.need, self.scale = t, None, need, None
+        self.sn = None  # (u, v) of the spectral norm whose 1/sigma is `scale`: d sigma / d weight = u v^T
 
     def add(self, g):
         self.g = g if self.g is None else self.g + g
@@ -138,7 +139,12 @@ def _conv_backward(x, W, b, dz, stride, padding, dx_ch):
         # with an epilogue scale s the layer computed conv(x, s * W): dL/dW = s * G and dL/ds = <G, W>, where
         # G = dz^T x is what the backward-weights GEMM produces (the s * lands in its layout-fixing copy)
         gw = nhwc.conv_wgrad(dz, xv, ks, stride=stride, padding=padding, scale=sc)
-        if sc is not None and W.scale.need:
+        if W.sn is not None:
+            # spectral norm, s = 1 / (u^T W v) with u, v constant: dL/dW = s G - s^2 <G, W> u v^T, and gw = s G
+            u, v = W.sn
+            k = torch.dot(gw.reshape(-1), W.t.reshape(-1)) * sc.reshape(())
+            gw.view(gw.shape[0], -1).addcmul_(u[:, None] * (-k), v[None, :])
+        elif sc is not None and W.scale.need:
             W.scale.add((torch.dot(gw.reshape(-1), W.t.reshape(-1)) / sc.reshape(())).reshape(sc.shape))
         W.add(gw)
     if b is not None and b.need:

@@ -254,6 +254,15 @@ int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kin
                              int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx,
                              int dx_Cs, int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad,
                              float slope, void* stream);
+/* Spectral normalisation (torch.nn.utils.spectral_norm as normalization.py:30-31 applies it) of n layers at once:
+ * `table` = n device-resident records of 8 x int64 {W fp32 [rows, cols] (weight_orig), u [rows], v [cols], rows, cols,
+ * first block of the layer in phase A (128 columns per block), first block in phase B (8 rows per block), offset
+ * of the layer's [u | v] copy in `snapshot` (may be NULL; the vectors the backward of this forward needs)}.
+ * training != 0: one power iteration, u and v updated in place (v <- normalize(W^T u), u <- normalize(W v)); then
+ * inv_sigma[i] = 1 / (u^T W v).  The normalised weight is never formed: cocos_tapconv takes inv_sigma as `scale`.
+ * scratch: 2n floats.  blocks_a / blocks_b: total blocks of the two phases. */
+int cocos_sn_power_iter(const void* table, int n, int blocks_a, int blocks_b, float* scratch, float* inv_sigma,
+                        float* snapshot, float eps, int training, void* stream);
 /* Per-pixel PONO statistics of x (kind 1|3) [npix, Cs] over its C channels: mean and 1/sqrt(unbiased var + eps)
  * (normalization.py:63-68), for the SPADE epilogue of cocos_tapconv. */
 int cocos_pono_stats_nhwc(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,

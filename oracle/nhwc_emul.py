@@ -124,6 +124,22 @@ class EmulBackend:
         if d["y_lo_off"]:
             y[..., d["y_lo_off"]:d["y_lo_off"] + C] = self._pad_reflect(z - hi, p).to(y.dtype)
 
+    def sn_power_iter(self, entries, training, eps):
+        """torch.nn.utils.spectral_norm.SpectralNorm.compute_weight up to (not including) weight / sigma, per layer."""
+        import torch.nn.functional as F
+        inv, shots, offs, snap = [], [], [], 0
+        with torch.no_grad():
+            for w, u, v in entries:
+                wm = w.reshape(w.shape[0], -1)
+                if training:
+                    v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps))
+                    u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=eps))
+                inv.append(1.0 / torch.dot(u, torch.mv(wm, v)))
+                shots += [u.clone(), v.clone()]
+                offs.append((snap, u.numel(), v.numel()))
+                snap += u.numel() + v.numel()
+        return torch.stack(inv), torch.cat(shots), offs
+
     def pono_stats(self, x, C, eps, mean, rstd):
         xf = x.t.float()[..., :C]
         m = xf.mean(3, keepdim=True)

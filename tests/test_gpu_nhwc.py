@@ -316,3 +316,36 @@ def test_conv_spade_epilogue(C, H, W, B, pad, xk, split):
 def F_conv(actv, w, b):
     a = torch.nn.functional.pad(actv.half().float(), (1, 1, 1, 1), mode="reflect")
     return torch.nn.functional.conv2d(a, w.half().float(), b)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_sn_power_iter_all_layers_at_once(training):
+    """cocos_sn_power_iter (one power iteration of torch.nn.utils.spectral_norm on every layer of a network in three
+    launches) against the per-layer torch expressions, for the weight shapes of the ade20k networks."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(1024, 1024, 3, 3), (512, 1024, 3, 3), (64, 3, 3, 3), (128, 64, 4, 4), (256, 512, 1, 1), (512, 256, 4, 4),
+              (407, 407, 3, 3)]
+
+    def make(dev):
+        gg = torch.Generator().manual_seed(21)
+        out = []
+        for s in shapes:
+            w = (torch.randn(s, generator=gg) * 0.05).to(dev)
+            u = torch.nn.functional.normalize(torch.randn(s[0], generator=gg), dim=0).to(dev)
+            v = torch.nn.functional.normalize(torch.randn(s[1] * s[2] * s[3], generator=gg), dim=0).to(dev)
+            out.append((w, u, v))
+        return out
+
+    ent_gpu, ent_cpu = make("cuda"), make("cpu")
+    inv_g, shot_g, offs_g = nhwc.backend().sn_power_iter(ent_gpu, training, 1e-12)
+    inv_g2, _, _ = nhwc.backend().sn_power_iter(ent_gpu, training, 1e-12)  # second call: cached table
+    inv_c, shot_c, offs_c = EmulBackend().sn_power_iter(ent_cpu, training, 1e-12)
+    _ = EmulBackend().sn_power_iter(ent_cpu, training, 1e-12)
+    torch.cuda.synchronize()
+    assert offs_g == offs_c
+    assert rel(inv_g, inv_c) < 1e-5
+    assert rel(shot_g, shot_c) < 1e-5
+    for (w, u, v), (wc, uc, vc) in zip(ent_gpu, ent_cpu):  # persistent vectors after two iterations
+        assert rel(u, uc) < 1e-4 and rel(v, vc) < 1e-4
+    if not training:
+        assert torch.equal(inv_g, inv_g2)
