@@ -213,27 +213,30 @@ int cocos_in_stats_nhwc(const void* x, int kind, int Cs, int B, int C, int HW, f
 int cocos_inst_act_nhwc_fwd(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
                             int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
                             int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
-                            void* stream) {
+                            const void* gb, int gb_kind, int gb_Cs, int batch_stats, void* stream) {
   if (!x || !stats || !y) {
     set_error("cocos_inst_act_nhwc_fwd: null pointer argument");
     return -1;
   }
   return inst_act_nhwc_fwd_launch(x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, y, y_kind, y_Cs,
-                                  y_lo_off, y_pad, y2, y2_Cs, B, C, H, W, eps, static_cast<cudaStream_t>(stream));
+                                  y_lo_off, y_pad, y2, y2_Cs, B, C, H, W, eps, gb, gb_kind, gb_Cs, batch_stats,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
                             int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
                             const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
                             int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
-                            void* stream) {
+                            const void* gb, int gb_kind, int gb_Cs, void* dgb, int dgb_Cs, int batch_stats,
+                            int const_stats, int phase, void* stream) {
   if (!dy || !x || !stats || !dx) {
     set_error("cocos_inst_act_nhwc_bwd: null pointer argument");
     return -1;
   }
   return inst_act_nhwc_bwd_launch(dy, dy_Cs, dy_pad, dy2, dy2_Cs, x, x_kind, x_Cs, stats, res, res_kind, res_Cs,
                                   slope_ptr, slope, bstats, dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C,
-                                  H, W, eps, static_cast<cudaStream_t>(stream));
+                                  H, W, eps, gb, gb_kind, gb_Cs, dgb, dgb_Cs, batch_stats, const_stats, phase,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,

@@ -86,12 +86,13 @@ int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, 
 int inst_act_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
                              int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
                              int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
-                             cudaStream_t stream);
+                             const void* gb, int gb_kind, int gb_Cs, int batch_stats, cudaStream_t stream);
 int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
                              int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
                              const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
                              int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
-                             cudaStream_t stream);
+                             const void* gb, int gb_kind, int gb_Cs, void* dgb, int dgb_Cs, int batch_stats,
+                             int const_stats, int phase, cudaStream_t stream);
 int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, int y_Cs, int pad, void* dz, int dz_Cs,
                         int B, int C, int H, int W, int act, float slope, cudaStream_t stream);
 int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,

@@ -257,11 +257,14 @@ __global__ void __launch_bounds__(256) spade_mod_nhwc_bwd_kernel(const SpadeBwd 
 struct Coef4 {
   float mean[4], rstd[4];
 };
-__device__ __forceinline__ Coef4 load_coef4(const float* __restrict__ stats, int b, int C, int c, float inv, float eps) {
+// stats [B or 1][C][2] = {sum, sumsq} over `1 / inv` values: per image (InstanceNorm2d) or, with bstride 0, over the
+// whole batch (BatchNorm2d in training mode; running statistics in eval mode are passed in the same form)
+__device__ __forceinline__ Coef4 load_coef4(const float* __restrict__ stats, int b, int C, int c, float inv, float eps,
+                                            int bstride = 1) {
   Coef4 k;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(b) * C + c + j) * 2);
+    const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(b) * bstride * C + c + j) * 2);
     k.mean[j] = st.x * inv;
     k.rstd[j] = rsqrtf(fmaxf(st.y * inv - k.mean[j] * k.mean[j], 0.f) + eps);
   }
@@ -319,6 +322,9 @@ struct InstFwd {
   void* y2; int y2_Cs;                   // optional second output: fp32 NHWC, no halo (residual source of the next block)
   int B, C, H, W;
   float eps;
+  // SPADE with instance / batch statistics (normalization.py:96-104,132-149): z = norm(x) * (1 + gamma) + beta
+  const void* gb; int gb_kind, gb_Cs;    // optional [gamma | beta] at channels [0,C) and [C,2C)
+  int batch_stats;                       // 1: stats are [1][C][2] over B*H*W values (BatchNorm2d)
 };
 
 // walks the (padded) OUTPUT pixels: halo pixels re-read their mirror source
@@ -331,7 +337,8 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_fwd_kernel(const InstFwd p,
   int p1 = p0 + pix_per_block;
   if (p1 > Hp * Wp) p1 = Hp * Wp;
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
-  const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / (p.H * p.W), p.eps);
+  const float cnt = p.batch_stats ? static_cast<float>(p.B) * p.H * p.W : static_cast<float>(p.H * p.W);
+  const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / cnt, p.eps, p.batch_stats ? 0 : 1);
 #pragma unroll 2
   for (int op = p0 + threadIdx.y; op < p1; op += 8) {
     const int ho = op / Wp, wo = op - ho * Wp;
@@ -340,11 +347,17 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_fwd_kernel(const InstFwd p,
     const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.res) t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
+    float4 g1 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gb) {
+      const float4 g = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + c), be = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + p.C + c);
+      g1 = make_float4(1.f + g.x, 1.f + g.y, 1.f + g.z, 1.f + g.w);
+      t.x += be.x; t.y += be.y; t.z += be.z; t.w += be.w;
+    }
     float4 o;
-    o.x = lrelu((v.x - k.mean[0]) * k.rstd[0] + t.x, slope);
-    o.y = lrelu((v.y - k.mean[1]) * k.rstd[1] + t.y, slope);
-    o.z = lrelu((v.z - k.mean[2]) * k.rstd[2] + t.z, slope);
-    o.w = lrelu((v.w - k.mean[3]) * k.rstd[3] + t.w, slope);
+    o.x = lrelu(fmaf((v.x - k.mean[0]) * k.rstd[0], g1.x, t.x), slope);
+    o.y = lrelu(fmaf((v.y - k.mean[1]) * k.rstd[1], g1.y, t.y), slope);
+    o.z = lrelu(fmaf((v.z - k.mean[2]) * k.rstd[2], g1.z, t.z), slope);
+    o.w = lrelu(fmaf((v.w - k.mean[3]) * k.rstd[3], g1.w, t.w), slope);
     const size_t yo = (static_cast<size_t>(b) * Hp * Wp + op) * p.y_Cs + c;
     st4(p.y, p.y_kind, yo, o);
     if (p.y_lo_off) st4(p.y, 1, yo + p.y_lo_off, lo4(o));
@@ -365,11 +378,15 @@ struct InstBwd {
   void* dres; int dres_Cs, dres_acc;     // optional bf16
   int B, C, H, W;
   float eps;
+  const void* gb; int gb_kind, gb_Cs;    // optional SPADE modulation [gamma | beta]
+  void* dgb; int dgb_Cs;                 // bf16 [B,H,W,dgb_Cs]: d gamma [0,C), d beta [C,2C) (pass 2 output)
+  int batch_stats;                       // statistics over the whole batch: stats / bstats are [1][C][2]
+  int const_stats;                       // eval-mode BatchNorm: the statistics do not depend on x (no mean terms)
 };
 
 // dz for 4 channels of one source pixel (shared by both passes)
 __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, int b, int pix, int c, float slope,
-                                            float* z, float* dz, float* u_neg_dy) {
+                                            float* z, float* dz, float* u_neg_dy, float* dact) {
   const size_t spix = static_cast<size_t>(b) * p.H * p.W + pix;
   float4 d;
   if (p.dy_pad) {
@@ -390,12 +407,19 @@ __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, in
     const float4 t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
     rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
   }
+  float g1[4] = {1.f, 1.f, 1.f, 1.f};
+  if (p.gb) {
+    const float4 g = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + c), be = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + p.C + c);
+    g1[0] += g.x; g1[1] += g.y; g1[2] += g.z; g1[3] += g.w;
+    rs[0] += be.x; rs[1] += be.y; rs[2] += be.z; rs[3] += be.w;
+  }
   const float in[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     z[j] = (in[j] - k.mean[j]) * k.rstd[j];
-    const float u = z[j] + rs[j];
-    dz[j] = u > 0.f ? dd[j] : dd[j] * slope;
+    const float u = fmaf(z[j], g1[j], rs[j]);
+    dact[j] = u > 0.f ? dd[j] : dd[j] * slope;   // gradient behind the activation: d beta, d residual
+    dz[j] = dact[j] * g1[j];                      // gradient of the normalised value
     u_neg_dy[j] = u > 0.f ? 0.f : dd[j] * u;
   }
 }
@@ -413,11 +437,12 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, ds = 0.f;
   if (c < p.C) {
-    const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / HW, p.eps);
+    const float cnt = p.batch_stats ? static_cast<float>(p.B) * HW : static_cast<float>(HW);
+    const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / cnt, p.eps, p.batch_stats ? 0 : 1);
 #pragma unroll 2
     for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
-      float z[4], dz[4], un[4];
-      inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un);
+      float z[4], dz[4], un[4], da[4];
+      inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un, da);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s[j] += dz[j];
@@ -444,8 +469,9 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
           bq += red[k][threadIdx.x][4 + j];
         }
         if (c + j < p.C) {
-          atomicAdd(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2, a);
-          atomicAdd(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2 + 1, bq);
+          const size_t bo = (static_cast<size_t>(p.batch_stats ? 0 : b) * p.C + c + j) * 2;
+          atomicAdd(p.bstats + bo, a);
+          atomicAdd(p.bstats + bo + 1, bq);
         }
       }
     }
@@ -468,22 +494,26 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const Inst
   int p1 = p0 + pix_per_block;
   if (p1 > HW) p1 = HW;
   const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
-  const float inv = 1.0f / HW;
-  const Coef4 k = load_coef4(p.stats, b, p.C, c, inv, p.eps);
+  const float inv = 1.0f / (p.batch_stats ? static_cast<float>(p.B) * HW : static_cast<float>(HW));
+  const Coef4 k = load_coef4(p.stats, b, p.C, c, inv, p.eps, p.batch_stats ? 0 : 1);
   float m1[4], m2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 bs = *reinterpret_cast<const float2*>(p.bstats + (static_cast<size_t>(b) * p.C + c + j) * 2);
-    m1[j] = bs.x * inv;
-    m2[j] = bs.y * inv;
+    const float2 bs = *reinterpret_cast<const float2*>(p.bstats + (static_cast<size_t>(p.batch_stats ? 0 : b) * p.C + c + j) * 2);
+    m1[j] = p.const_stats ? 0.f : bs.x * inv;
+    m2[j] = p.const_stats ? 0.f : bs.y * inv;
   }
 #pragma unroll 2
   for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
-    float z[4], dz[4], un[4], o[4];
-    inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un);
+    float z[4], dz[4], un[4], o[4], da[4];
+    inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un, da);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = k.rstd[j] * (dz[j] - m1[j] - z[j] * m2[j]);
     const size_t spix = static_cast<size_t>(b) * HW + pix;
+    if (p.dgb) {
+      st4(p.dgb, 2, spix * p.dgb_Cs + c, make_float4(da[0] * z[0], da[1] * z[1], da[2] * z[2], da[3] * z[3]));
+      st4(p.dgb, 2, spix * p.dgb_Cs + p.C + c, make_float4(da[0], da[1], da[2], da[3]));
+    }
     float4 t = make_float4(o[0], o[1], o[2], o[3]);
     if (p.dx_acc) {
       const float4 old = ld4(p.dx, 2, spix * p.dx_Cs + c);
@@ -491,7 +521,7 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const Inst
     }
     st4(p.dx, 2, spix * p.dx_Cs + c, t);
     if (p.dres) {
-      float4 t2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      float4 t2 = make_float4(da[0], da[1], da[2], da[3]);
       if (p.dres_acc) {
         const float4 old = ld4(p.dres, 2, spix * p.dres_Cs + c);
         t2.x += old.x; t2.y += old.y; t2.z += old.z; t2.w += old.w;
@@ -870,15 +900,16 @@ int in_stats_nhwc_launch(const void* x, int kind, int Cs, int B, int C, int HW, 
 int inst_act_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
                              int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
                              int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
-                             cudaStream_t stream) {
+                             const void* gb, int gb_kind, int gb_Cs, int batch_stats, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || (C % 4) || (x_Cs % 4) || (y_Cs % 4) || (y_lo_off % 4) || H <= y_pad || W <= y_pad ||
       y_pad < 0 || y_pad > 1 || x_kind < 1 || x_kind > 3 || y_kind < 1 || y_kind > 3 || (y_lo_off && y_kind != 1) ||
-      (res && (res_kind < 1 || res_kind > 3 || (res_Cs % 4))) || (y2 && (y2_Cs % 4))) {
+      (res && (res_kind < 1 || res_kind > 3 || (res_Cs % 4))) || (y2 && (y2_Cs % 4)) ||
+      (gb && ((gb_kind != 1 && gb_kind != 3) || (gb_Cs % 4) || gb_Cs < 2 * C))) {
     set_error("inst_act_nhwc_fwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, y_pad);
     return -1;
   }
   InstFwd p{x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, y, y_kind, y_Cs, y_lo_off, y_pad,
-            y2, y2_Cs, B, C, H, W, eps};
+            y2, y2_Cs, B, C, H, W, eps, gb, gb_kind, gb_Cs, batch_stats};
   dim3 grid, block;
   int ppb;
   stats_grid((H + 2 * y_pad) * (W + 2 * y_pad), C, B, &grid, &block, &ppb);
@@ -891,23 +922,31 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
                              int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
                              const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
                              int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
-                             cudaStream_t stream) {
+                             const void* gb, int gb_kind, int gb_Cs, void* dgb, int dgb_Cs, int batch_stats,
+                             int const_stats, int phase, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || (C % 4) || (dy_Cs % 4) || (x_Cs % 4) || (dx_Cs % 4) || H <= dy_pad || W <= dy_pad ||
       dy_pad < 0 || dy_pad > 1 || x_kind < 1 || x_kind > 3 || (res && (res_kind < 1 || res_kind > 3 || (res_Cs % 4))) ||
-      (dy2 && (dy2_Cs % 4)) || (dres && (dres_Cs % 4)) || !bstats) {
+      (dy2 && (dy2_Cs % 4)) || (dres && (dres_Cs % 4)) || !bstats || phase < 0 || phase > 2 ||
+      (gb && ((gb_kind != 1 && gb_kind != 3) || (gb_Cs % 4) || gb_Cs < 2 * C || !dgb || (dgb_Cs % 4) || dgb_Cs < 2 * C))) {
     set_error("inst_act_nhwc_bwd: bad arguments (B=%d C=%d H=%d W=%d pad=%d)", B, C, H, W, dy_pad);
     return -1;
   }
   InstBwd p{dy, dy_Cs, dy_pad, dy2, dy2_Cs, x, x_kind, x_Cs, stats, res, res_kind, res_Cs, slope_ptr, slope, bstats,
-            dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C, H, W, eps};
-  COCOS_CUDA_CHECK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * B * C, stream));
+            dslope, dx, dx_Cs, dx_acc, dres, dres_Cs, dres_acc, B, C, H, W, eps, gb, gb_kind, gb_Cs, dgb, dgb_Cs,
+            batch_stats, const_stats};
   dim3 grid, block;
   int ppb;
   stats_grid(H * W, C, B, &grid, &block, &ppb);
-  inst_act_nhwc_bwd_stats_kernel<<<grid, block, 0, stream>>>(p, ppb);
-  COCOS_CUDA_CHECK(cudaGetLastError());
-  inst_act_nhwc_bwd_apply_kernel<<<grid, block, 0, stream>>>(p, ppb);
-  COCOS_CUDA_CHECK(cudaGetLastError());
+  // phase 1: statistics only, phase 2: apply only (a synchronised BatchNorm all-reduces bstats in between), 0: both
+  if (phase != 2) {
+    COCOS_CUDA_CHECK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * (batch_stats ? 1 : B) * C, stream));
+    inst_act_nhwc_bwd_stats_kernel<<<grid, block, 0, stream>>>(p, ppb);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+  }
+  if (phase != 1) {
+    inst_act_nhwc_bwd_apply_kernel<<<grid, block, 0, stream>>>(p, ppb);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -77,7 +77,7 @@ class ParamSet:
         (nhwc.conv_spade), else [gamma | beta]."""
         self.conv(m.mlp_shared[1])
         C = m.mlp_gamma.out_channels
-        W = nhwc.spade_interleave(C) if fused_spade() else 0
+        W = nhwc.spade_interleave(C) if (fused_spade() and m.pono) else 0
         if W:
             self._add(("w", id(m)), nhwc.interleave_rows(m.mlp_gamma.weight, m.mlp_beta.weight, W))
             self._add(("b", id(m)), nhwc.interleave_rows(m.mlp_gamma.bias, m.mlp_beta.bias, W))
@@ -146,7 +146,9 @@ def _dev_ok(t):
 
 
 def spade_supported(norm):
-    return norm.pono and norm.mlp_gamma.kernel_size == (3, 3)
+    pf = norm.param_free_norm
+    stat = isinstance(pf, (nn.InstanceNorm2d, nn.BatchNorm2d)) and not pf.affine and norm.mlp_gamma.out_channels % 4 == 0
+    return (norm.pono or stat) and norm.mlp_gamma.kernel_size == (3, 3)
 
 
 def block_supported(blk):
@@ -172,6 +174,9 @@ def spade_norm(tp, ps, norm, x, pyr, mode, slope, pad):
     shared = norm.mlp_shared[1]
     actv = T.conv(tp, seg, ps.w(shared), ps.b(shared), act=ACT_RELU, out_kind=F16, out_pad=1, split_out=mode.split,
                   dx_ch=pyr.grad_ch, wsplit=mode.split)
+    if not norm.pono:  # instance / batch statistics: gamma|beta convolution + one modulating norm kernel
+        gb = T.conv(tp, actv, ps.w(norm), ps.b(norm), out_kind=mode.raw)
+        return T.spade_stat(tp, x, gb, norm.param_free_norm, pad, slope, mode.split)
     if fused_spade() and nhwc.spade_interleave(C):
         return T.spade_conv(tp, x, actv, ps.w(norm), ps.b(norm), C, pad, slope, mode.split, gb_kind=mode.raw)
     gb = T.conv(tp, actv, ps.w(norm), ps.b(norm), out_kind=mode.raw)
@@ -283,9 +288,10 @@ def adaptor_forward(net, x, precise=True):
     mode = T.PRECISE if precise else T.FAST
     layers = [net.layer1, net.layer2, net.layer3, net.layer4, net.layer5]
     blocks = [net.head_0, net.G_middle_0, net.G_middle_1]
-    # a one-hot label map is exact in fp16: no lo term for the activations, only for the weights
-    is_image = x.shape[1] <= 4
-    xsplit = mode.split and is_image
+    # a one-hot label map is exact in fp16: no lo term for the activations, only for the weights (images, the float
+    # pose / edge maps of deepfashion / celebahqedge and noised label maps carry one)
+    exact = x.shape[1] > 4 and net.opt.dataset_mode not in ("deepfashion", "celebahqedge") and not net.opt.mask_noise
+    xsplit = mode.split and not exact
     ps = ParamSet()
     for l in layers:
         ps.conv(l[0])

@@ -235,20 +235,24 @@ class NativeBackend:
         _lib.check(self.lib.cocos_in_stats_nhwc(x.t.data_ptr(), x.kind, x.Cs, x.B, C, x.H * x.W, stats.data_ptr(),
                                                 _stream()), "cocos_in_stats_nhwc", kernels=2)
 
-    def inst_fwd(self, x, stats, res, slope_ptr, slope, y, y2, eps, C):
+    def inst_fwd(self, x, stats, res, slope_ptr, slope, y, y2, eps, C, gb=None, batch_stats=False):
         _lib.check(self.lib.cocos_inst_act_nhwc_fwd(
             x.t.data_ptr(), x.kind, x.Cs, stats.data_ptr(), _p(res.t if res else None), res.kind if res else 0,
             res.Cs if res else 0, _p(slope_ptr), float(slope), y.t.data_ptr(), y.kind, y.Cs, y.lo, y.pad,
-            _p(y2.t if y2 else None), y2.Cs if y2 else 0, x.B, C, x.H, x.W, float(eps), _stream()),
+            _p(y2.t if y2 else None), y2.Cs if y2 else 0, x.B, C, x.H, x.W, float(eps),
+            _p(gb.t if gb else None), gb.kind if gb else 0, gb.Cs if gb else 0, int(batch_stats), _stream()),
             "cocos_inst_act_nhwc_fwd")
 
-    def inst_bwd(self, dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C):
+    def inst_bwd(self, dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C,
+                 gb=None, dgb=None, batch_stats=False, const_stats=False, phase=0):
         _lib.check(self.lib.cocos_inst_act_nhwc_bwd(
             dy.t.data_ptr(), dy.Cs, dy.pad, _p(dy2.t if dy2 else None), dy2.Cs if dy2 else 0, x.t.data_ptr(), x.kind,
             x.Cs, stats.data_ptr(), _p(res.t if res else None), res.kind if res else 0, res.Cs if res else 0,
             _p(slope_ptr), float(slope), bstats.data_ptr(), _p(dslope), dx.t.data_ptr(), dx.Cs, int(dx_acc),
             _p(dres.t if dres else None), dres.Cs if dres else 0, int(dres_acc), x.B, C, x.H, x.W, float(eps),
-            _stream()), "cocos_inst_act_nhwc_bwd", kernels=3)
+            _p(gb.t if gb else None), gb.kind if gb else 0, gb.Cs if gb else 0, _p(dgb.t if dgb else None),
+            dgb.Cs if dgb else 0, int(batch_stats), int(const_stats), int(phase), _stream()),
+            "cocos_inst_act_nhwc_bwd", kernels=3 if phase == 0 else (2 if phase == 1 else 1))
 
     def act_bwd(self, dy, y, dz, C, act, slope):
         _lib.check(self.lib.cocos_act_bwd_nhwc(dy.t.data_ptr(), dy.Cs, y.t.data_ptr(), y.kind, y.Cs, y.pad,
@@ -424,10 +428,10 @@ def spade_interleave(C):
 def interleave_rows(gamma, beta, W):
     """[C, ...] gamma rows and beta rows -> [2C, ...] ordered per 2W rows as [gamma of W channels | beta of the same]."""
     C = gamma.shape[0]
-    parts = []
-    for c0 in range(0, C, W):
-        parts += [gamma[c0:c0 + W], beta[c0:c0 + W]]
-    return torch.cat(parts, 0)
+    rest = tuple(gamma.shape[1:])
+    # one stack (its backward is two views of the gradient), not 2C/W slices (each slice's backward materialises a
+    # full-size zero tensor)
+    return torch.stack((gamma.reshape((C // W, W) + rest), beta.reshape((C // W, W) + rest)), 1).reshape((2 * C,) + rest)
 
 
 def conv_spade(actv, weight, bias, x, C, pad, slope, eps=1e-5, split_out=False, want_gb=True, gb_kind=F16, wsplit=None):
@@ -560,18 +564,21 @@ def in_stats(x):
 
 
 def inst_act_fwd(x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, out_kind=F16, out_pad=0, split_out=False,
-                 want_raw=False):
-    """y = act(IN(x) [+ res]); returns (y NT, y2 NT | None): y2 = fp32 copy without halo (want_raw)."""
-    assert x.pad == 0
+                 want_raw=False, gb=None, batch_stats=False):
+    """y = act(norm(x) [* (1 + gamma) + beta] [+ res]); stats per image ([B,C4,2], InstanceNorm2d) or over the batch
+    ([1,C4,2], batch_stats: BatchNorm2d); gb = [gamma | beta] NT: SPADE with those statistics (normalization.py:96-104).
+    Returns (y NT, y2 NT | None): y2 = fp32 copy without halo (want_raw)."""
+    assert x.pad == 0 and (gb is None or (gb.pad == 0 and gb.C == 2 * x.C and x.C % 4 == 0))
     y = new(x.B, x.H, x.W, x.C, out_kind, x.t.device, pad=out_pad, split=split_out, zero=False)
     y2 = new(x.B, x.H, x.W, x.C, F32, x.t.device, zero=False) if want_raw else None
-    backend().inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, round_up(x.C, 4))
+    backend().inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, round_up(x.C, 4), gb=gb, batch_stats=batch_stats)
     return y, y2
 
 
 def inst_act_bwd(dy, x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, dy2=None, dx=None, want_dres=False,
-                 dres=None, dslope=None):
-    """-> (dx bf16, dres bf16 | None).  dx / dres given: accumulate."""
+                 dres=None, dslope=None, gb=None, batch_stats=False, const_stats=False, reduce_bstats=None):
+    """-> (dx bf16, dres bf16 | None, dgb bf16 | None).  dx / dres given: accumulate.  reduce_bstats: callable applied
+    to the [1,C4,2] reduction between the two passes (the all-reduce of a synchronised BatchNorm)."""
     assert dy.kind == BF16
     c4 = round_up(x.C, 4)
     dx_acc = dx is not None
@@ -580,7 +587,15 @@ def inst_act_bwd(dy, x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, dy
     dres_acc = dres is not None
     if want_dres and dres is None:
         dres = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=False)
-    bstats = torch.empty((x.B, c4, 2), dtype=torch.float32, device=x.t.device)
-    backend().inst_bwd(dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc,
-                       dres if want_dres else None, dres_acc, eps, c4)
-    return dx, (dres if want_dres else None)
+    dgb = new(x.B, x.H, x.W, 2 * x.C, BF16, x.t.device, zero=False) if gb is not None else None
+    bstats = torch.empty((1 if batch_stats else x.B, c4, 2), dtype=torch.float32, device=x.t.device)
+    args = (dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres if want_dres else None, dres_acc,
+            eps, c4)
+    kw = dict(gb=gb, dgb=dgb, batch_stats=batch_stats, const_stats=const_stats)
+    if reduce_bstats is None:
+        backend().inst_bwd(*args, **kw)
+    else:
+        backend().inst_bwd(*args, phase=1, **kw)
+        reduce_bstats(bstats)
+        backend().inst_bwd(*args, phase=2, **kw)
+    return dx, (dres if want_dres else None), dgb

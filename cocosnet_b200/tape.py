@@ -263,7 +263,7 @@ def inst_act(tp, x, slope=1.0, prelu=None, res=None, eps=1e-5, out_kind=F16, out
         if prelu is not None and prelu.need:
             dslope = torch.zeros((), dtype=torch.float32, device=y.t.device)
         want_dres = res is not None and res.need
-        dx, dres = nhwc.inst_act_bwd(g, x.v, stats, slope=slope, slope_ptr=sp, res=None if res is None else res.v,
+        dx, dres, _ = nhwc.inst_act_bwd(g, x.v, stats, slope=slope, slope_ptr=sp, res=None if res is None else res.v,
                                      eps=eps, dy2=g2, dx=x.g if x.need else None, want_dres=want_dres,
                                      dres=res.g if want_dres else None, dslope=dslope)
         if x.need:
@@ -274,6 +274,65 @@ def inst_act(tp, x, slope=1.0, prelu=None, res=None, eps=1e-5, out_kind=F16, out
             prelu.add(dslope.reshape(prelu.t.shape))
     tp.add(bwd)
     return out, out2
+
+
+def _avg_over_ranks(t):
+    """In-place mean over the data-parallel ranks (SynchronizedBatchNorm2d semantics: statistics of the global batch)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t)
+            t.div_(dist.get_world_size())
+
+
+def spade_stat(tp, x, gb, pnorm, pad, slope, split):
+    """SPADE whose parameter-free norm is InstanceNorm2d or (Sync)BatchNorm2d (normalization.py:96-104,132-149: every
+    configuration without --PONO): raw x, raw gb = [gamma | beta] -> op = reflect_pad(lrelu(norm(x) (1 + gamma) + beta)).
+    BatchNorm2d: batch statistics in training mode (averaged over the ranks, running estimates updated like
+    nn.BatchNorm2d does), running estimates in eval mode."""
+    import torch.nn as nn
+    xv = x.v
+    C, c4 = xv.C, nhwc.round_up(xv.C, 4)
+    batch = isinstance(pnorm, nn.BatchNorm2d)
+    const = False
+    if not batch:
+        stats = nhwc.in_stats(xv)
+    elif pnorm.training or pnorm.running_mean is None:
+        stats = nhwc.in_stats(xv).sum(0, keepdim=True)
+        _avg_over_ranks(stats)
+        if pnorm.running_mean is not None:
+            with torch.no_grad():
+                n = xv.B * xv.H * xv.W
+                mean = stats[0, :C, 0] / n
+                var = (stats[0, :C, 1] / n - mean * mean).clamp_min_(0)
+                mom = pnorm.momentum if pnorm.momentum is not None else 0.1
+                pnorm.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                pnorm.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+                if pnorm.num_batches_tracked is not None:
+                    pnorm.num_batches_tracked += 1
+    else:  # eval: the running estimates, in the (sum, sum of squares) form the kernels take
+        n = float(xv.B * xv.H * xv.W)
+        stats = torch.zeros((1, c4, 2), dtype=torch.float32, device=xv.t.device)
+        stats[0, :C, 0] = pnorm.running_mean * n
+        stats[0, :C, 1] = (pnorm.running_var + pnorm.running_mean ** 2) * n
+        const = True
+    y, _ = nhwc.inst_act_fwd(xv, stats, slope=slope, eps=pnorm.eps, out_kind=F16, out_pad=pad, split_out=split, gb=gb.v,
+                             batch_stats=batch)
+    out = Var(y)
+
+    def bwd():
+        if out.g is None:
+            return
+        dx, _, dgb = nhwc.inst_act_bwd(out.g, xv, stats, slope=slope, eps=pnorm.eps, dx=x.g if x.need else None, gb=gb.v,
+                                       batch_stats=batch, const_stats=const,
+                                       reduce_bstats=_avg_over_ranks if (batch and not const) else None)
+        if x.need:
+            x.g = dx
+        acc(gb, dgb)
+    tp.add(bwd)
+    return out
 
 
 def maxpool(tp, x):

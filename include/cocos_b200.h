@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define COCOS_ABI_VERSION 5
+#define COCOS_ABI_VERSION 6
 
 int cocos_abi_version(void);
 const char* cocos_last_error(void);
@@ -278,12 +278,19 @@ int cocos_in_stats_nhwc(const void* x, int kind, int Cs, int B, int C, int HW, f
 int cocos_inst_act_nhwc_fwd(const void* x, int x_kind, int x_Cs, const float* stats, const void* res, int res_kind,
                             int res_Cs, const float* slope_ptr, float slope, void* y, int y_kind, int y_Cs,
                             int y_lo_off, int y_pad, void* y2, int y2_Cs, int B, int C, int H, int W, float eps,
-                            void* stream);
+                            const void* gb, int gb_kind, int gb_Cs, int batch_stats, void* stream);
 int cocos_inst_act_nhwc_bwd(const void* dy, int dy_Cs, int dy_pad, const void* dy2, int dy2_Cs, const void* x,
                             int x_kind, int x_Cs, const float* stats, const void* res, int res_kind, int res_Cs,
                             const float* slope_ptr, float slope, float* bstats, float* dslope, void* dx, int dx_Cs,
                             int dx_acc, void* dres, int dres_Cs, int dres_acc, int B, int C, int H, int W, float eps,
-                            void* stream);
+                            const void* gb, int gb_kind, int gb_Cs, void* dgb, int dgb_Cs, int batch_stats,
+                            int const_stats, int phase, void* stream);
+/* The same two entry points serve SPADE with instance / batch statistics (normalization.py:96-104,132-149, the
+ * celebahq / deepfashion configurations): gb (kind 1|3, [B,H,W,gb_Cs], gamma at channels [0,C), beta at [C,2C))
+ * modulates the normalised value, z = norm(x) * (1 + gamma) + beta, and the backward also emits dgb (bf16);
+ * batch_stats = 1: stats / bstats are [1][C][2] over B*H*W values (BatchNorm2d, training); const_stats = 1: the
+ * statistics are constants (running estimates, eval mode); phase 1 / 2 = only the reduction / only the apply pass
+ * (a synchronised BatchNorm all-reduces bstats in between), 0 = both. */
 
 /* Backward of an activation fused into a cocos_tapconv epilogue (act 1 ReLU: normalization.py:114-117, correspondence.py
  * 107-146; act 2 LeakyReLU: discriminator.py:93): dz[b,h,w,c] = fold_halo(dy)[b,h,w,c] * act'(y[b,h+pad,w+pad,c]);

@@ -245,15 +245,18 @@ class EmulBackend:
         stats[..., 1] = (xf * xf).sum((1, 2))
 
     @staticmethod
-    def _in_norm(x, stats, eps, C):
-        hw = x.H * x.W
-        mean = stats[..., 0] / hw
-        var = (stats[..., 1] / hw - mean * mean).clamp_min(0)
+    def _in_norm(x, stats, eps, C, batch_stats=False):
+        cnt = x.H * x.W * (x.B if batch_stats else 1)
+        mean = stats[..., 0] / cnt
+        var = (stats[..., 1] / cnt - mean * mean).clamp_min(0)
         r = (var + eps).rsqrt()
         return (x.t.float()[..., :C] - mean[:, None, None]) * r[:, None, None], r[:, None, None]
 
-    def inst_fwd(self, x, stats, res, slope_ptr, slope, y, y2, eps, C):
-        z, _ = self._in_norm(x, stats, eps, C)
+    def inst_fwd(self, x, stats, res, slope_ptr, slope, y, y2, eps, C, gb=None, batch_stats=False):
+        z, _ = self._in_norm(x, stats, eps, C, batch_stats)
+        if gb is not None:
+            g = gb.t.float()
+            z = z * (1 + g[..., :C]) + g[..., C:2 * C]
         u = z + (res.t.float()[..., :C] if res is not None else 0)
         a = float(slope_ptr) if slope_ptr is not None else slope
         o = torch.where(u > 0, u, u * a)
@@ -261,25 +264,43 @@ class EmulBackend:
         if y2 is not None:
             y2.t[..., :C] = o
 
-    def inst_bwd(self, dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C):
+    def inst_bwd(self, dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C,
+                 gb=None, dgb=None, batch_stats=False, const_stats=False, phase=0):
         d = self._fold(dy.t.float()[..., :C], dy.pad)
         if dy2 is not None:
             d = d + dy2.t.float()[..., :C]
-        z, r = self._in_norm(x, stats, eps, C)
-        u = z + (res.t.float()[..., :C] if res is not None else 0)
+        z, r = self._in_norm(x, stats, eps, C, batch_stats)
+        g1 = 1.0
+        u = z
+        if gb is not None:
+            g = gb.t.float()
+            g1 = 1 + g[..., :C]
+            u = z * g1 + g[..., C:2 * C]
+        u = u + (res.t.float()[..., :C] if res is not None else 0)
         a = float(slope_ptr) if slope_ptr is not None else slope
-        dz = torch.where(u > 0, d, d * a)
-        if dslope is not None:
-            dslope += torch.where(u > 0, torch.zeros_like(u), d * u).sum()
-        hw = x.H * x.W
-        bstats[..., 0] = dz.sum((1, 2))
-        bstats[..., 1] = (dz * z).sum((1, 2))
-        out = r * (dz - bstats[..., 0][:, None, None] / hw - z * bstats[..., 1][:, None, None] / hw)
+        da = torch.where(u > 0, d, d * a)
+        dz = da * g1
+        cnt = x.H * x.W * (x.B if batch_stats else 1)
+        red = (0, 1, 2) if batch_stats else (1, 2)
+        if phase != 2:
+            if dslope is not None:
+                dslope += torch.where(u > 0, torch.zeros_like(u), d * u).sum()
+            bstats[..., 0] = dz.sum(red, keepdim=batch_stats).reshape(bstats[..., 0].shape)
+            bstats[..., 1] = (dz * z).sum(red, keepdim=batch_stats).reshape(bstats[..., 1].shape)
+        if phase == 1:
+            return
+        m1, m2 = bstats[..., 0][:, None, None] / cnt, bstats[..., 1][:, None, None] / cnt
+        if const_stats:
+            m1, m2 = 0.0, 0.0
+        out = r * (dz - m1 - z * m2)
         if dx_acc:
             out = out + dx.t.float()[..., :C]
         dx.t[..., :C] = out.to(dx.t.dtype)
+        if dgb is not None:
+            dgb.t[..., :C] = (da * z).to(dgb.t.dtype)
+            dgb.t[..., C:2 * C] = da.to(dgb.t.dtype)
         if dres is not None:
-            o2 = dz + (dres.t.float()[..., :C] if dres_acc else 0)
+            o2 = da + (dres.t.float()[..., :C] if dres_acc else 0)
             dres.t[..., :C] = o2.to(dres.t.dtype)
 
     def act_bwd(self, dy, y, dz, C, act, slope):

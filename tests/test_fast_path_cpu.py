@@ -25,7 +25,7 @@ class CountingEmul(EmulBackend):
     def __init__(self):
         super().__init__(exact=True)
         self.calls = {"tapconv": 0, "tapwgrad": 0, "spade_fwd": 0, "inst_fwd": 0, "maxpool_fwd": 0, "maxpool_bwd": 0,
-                      "stride2": 0, "spade_epilogue": 0}
+                      "stride2": 0, "spade_epilogue": 0, "inst_mod": 0}
 
     def maxpool_fwd(self, *a, **k):
         self.calls["maxpool_fwd"] += 1
@@ -51,17 +51,30 @@ class CountingEmul(EmulBackend):
 
     def inst_fwd(self, *a, **k):
         self.calls["inst_fwd"] += 1
+        self.calls["inst_mod"] += int(k.get("gb") is not None)
         return super().inst_fwd(*a, **k)
 
 
+CONFIGS = {
+    "ade20k_train": ADE_TRAIN,
+    # no --PONO: SPADE with (Sync)BatchNorm statistics, adaptor_kernel 4, bilinear warp, cycle term
+    "celebahq_train": ["--dataset_mode", "celebahq", "--warp_bilinear", "--adaptor_kernel", "4", "--warp_cycle_w", "1.0",
+                       "--batchSize", "1", "--gpu_ids", "-1"],
+    # float pose maps as the label input (split operands from the first layer on), folded patch warp
+    "deepfashion_train": ["--dataset_mode", "deepfashion", "--warp_patch", "--video_like", "--batchSize", "1",
+                          "--gpu_ids", "-1"],
+}
+
+
 @pytest.mark.timeout(1200)
-def test_ade20k_train_step_on_the_tape_matches_reference_golden():
+@pytest.mark.parametrize("config", list(CONFIGS))
+def test_train_step_on_the_tape_matches_reference_golden(config):
     from cocosnet_b200.pix2pix_model import Pix2PixModel
     be = CountingEmul()
     old = nhwc.set_backend(be)
     try:
-        gold = np.load(os.path.join(GOLD, "model_ade20k_train.npz"))
-        opt = TrainOptions().parse(ADE_TRAIN, save=False, verbose=False)
+        gold = np.load(os.path.join(GOLD, "model_%s.npz" % config))
+        opt = TrainOptions().parse(CONFIGS[config], save=False, verbose=False)
         opt.verbose_networks = False
         opt.allow_random_vgg = True
         torch.manual_seed(0)
@@ -77,9 +90,13 @@ def test_ade20k_train_step_on_the_tape_matches_reference_golden():
     finally:
         nhwc.set_backend(old)
     # the networks really ran on the tape: 3 adaptor passes x (5 + 24) convs, 7 generator blocks, the residual stack ...
-    # every SPADE layer modulates in the epilogue of its gamma|beta convolution (no separate modulation pass)
-    assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_epilogue"] > 30 \
-        and be.calls["spade_fwd"] == 0, be.calls
+    assert be.calls["tapconv"] > 200 and be.calls["tapwgrad"] > 100 and be.calls["spade_fwd"] == 0, be.calls
+    if config == "ade20k_train":
+        # --PONO: every SPADE layer modulates in the epilogue of its gamma|beta convolution (no separate pass)
+        assert be.calls["spade_epilogue"] > 30, be.calls
+    else:
+        # batch statistics: gamma|beta convolution + ONE modulating norm kernel per SPADE layer
+        assert be.calls["spade_epilogue"] == 0 and be.calls["inst_mod"] > 30, be.calls
     # ... the VGG19 feature net (3 forward passes x 4 poolings, one backward) and both PatchGANs (3 stride-2 4x4
     # convolutions each, G step: fake + real halves, D step: one batch)
     assert be.calls["maxpool_fwd"] == 12 and be.calls["maxpool_bwd"] == 4 and be.calls["stride2"] >= 18, be.calls

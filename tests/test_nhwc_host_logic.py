@@ -149,7 +149,7 @@ def test_inst_act_matches_autograd(emul, pad, prelu, with_res):
     dy = nhwc.pack(gy, nhwc.BF16)
     dy.pad = pad
     dslope = torch.zeros(()) if prelu else None
-    dx, dres = nhwc.inst_act_bwd(dy, xn, st, slope=0.2, slope_ptr=aptr, res=rn, dy2=nhwc.pack(gy2, nhwc.BF16),
+    dx, dres, _ = nhwc.inst_act_bwd(dy, xn, st, slope=0.2, slope_ptr=aptr, res=rn, dy2=nhwc.pack(gy2, nhwc.BF16),
                                  want_dres=with_res, dslope=dslope)
     assert rel(nt_to_nchw(dx), x.grad) < tol(emul)
     if with_res:
