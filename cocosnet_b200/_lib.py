@@ -37,6 +37,8 @@ SIGNATURES = {
                                 + [_c_float, _c_float, _vp],
     "cocos_spade_mod_nhwc_bwd": [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int,
                                  _c_int, _vp, _c_int] + [_c_int] * 5 + [_c_float, _vp],
+    "cocos_ctx_rows_fwd": [_vp, _vp, _c_int, _c_int, _c_float, _c_float, _vp],
+    "cocos_ctx_rows_bwd": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_float, _c_float, _vp],
     "cocos_sn_power_iter": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_float, _c_int, _vp],
     "cocos_pono_stats_nhwc": [_vp, _c_int, _c_int, _c_int, _c_ll, _c_float, _vp, _vp, _vp],
     "cocos_in_stats_nhwc": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],

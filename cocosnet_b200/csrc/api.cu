@@ -175,6 +175,23 @@ int cocos_spade_mod_nhwc_fwd(const void* x, int x_kind, int x_Cs, const void* gb
                                    slope, eps, static_cast<cudaStream_t>(stream));
 }
 
+int cocos_ctx_rows_fwd(const float* S, float* cx, int B, int N, float h, float eps, void* stream) {
+  if (!S || !cx) {
+    set_error("cocos_ctx_rows_fwd: null pointer argument");
+    return -1;
+  }
+  return ctx_rows_fwd_launch(S, cx, B, N, h, eps, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_ctx_rows_bwd(const float* S, const float* g, void* dS, int B, int N, int ldd, float h, float eps,
+                       void* stream) {
+  if (!S || !g || !dS) {
+    set_error("cocos_ctx_rows_bwd: null pointer argument");
+    return -1;
+  }
+  return ctx_rows_bwd_launch(S, g, dS, B, N, ldd, h, eps, static_cast<cudaStream_t>(stream));
+}
+
 int cocos_sn_power_iter(const void* table, int n, int blocks_a, int blocks_b, float* scratch, float* inv_sigma,
                         float* snapshot, float eps, int training, void* stream) {
   return sn_power_iter_launch(table, n, blocks_a, blocks_b, scratch, inv_sigma, snapshot, eps, training,

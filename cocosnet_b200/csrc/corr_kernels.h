@@ -74,6 +74,9 @@ int tapwgrad_launch(const cocos_tapwgrad_desc* d, cudaStream_t stream);
 int spade_mod_nhwc_fwd_launch(const void* x, int x_kind, int x_Cs, const void* gb, int gb_kind, int gb_Cs, void* y,
                               int y_Cs, int y_lo_off, float* mean, float* rstd, int B, int C, int H, int W, int pad,
                               float slope, float eps, cudaStream_t stream);
+int ctx_rows_fwd_launch(const float* S, float* cx, int B, int N, float h, float eps, cudaStream_t stream);
+int ctx_rows_bwd_launch(const float* S, const float* g, void* dS, int B, int N, int ldd, float h, float eps,
+                        cudaStream_t stream);
 int sn_power_iter_launch(const void* table, int n, int blocks_a, int blocks_b, float* scratch, float* inv_sigma,
                          float* snapshot, float eps, int training, cudaStream_t stream);
 int pono_stats_nhwc_launch(const void* x, int kind, int Cs, int C, long long npix, float eps, float* mean, float* rstd,

@@ -43,6 +43,35 @@ class GANLoss(nn.Module):
         return total / len(x)
 
 
+class _CtxRows(torch.autograd.Function):
+    """cx[b,i] = max_j A_ij from the normalised features: the N x N part of the contextual loss on hand-written
+    kernels -- S = Xhat^T Yhat on the tcgen05 GEMM (3-term split fp16 operands: the loss divides by min_j (1 - S)),
+    one warp per row for min / exp / sum, and in the backward dS (bf16) + one more GEMM for dXhat.  The reference keeps
+    d, d_norm, w, A ([B,N,N] fp32 each) and their autograd copies."""
+
+    @staticmethod
+    def forward(ctx, x, y, h):
+        from .. import ops
+        S = ops.gemm_f16(ops.pack_rows(x.contiguous(), split=1), ops.pack_rows(y.contiguous(), split=2))
+        ctx.save_for_backward(y, S)
+        ctx.h = h
+        return ops.ctx_rows_fwd(S, h)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import ops
+        y, S = ctx.saved_tensors
+        ds = ops.ctx_rows_bwd(S, g, ctx.h)
+        # dXhat^T [C, N_i] = Yhat_cm [C, N_j] . dS^T
+        return ops.gemm_f16(ops.cast_rows(y.contiguous(), torch.bfloat16), ds), None, None
+
+
+def _ctx_rows_native(x, y):
+    from .. import ops
+    return (x.is_cuda and x.dtype == torch.float32 and not ops.STOCK_TORCH and x.shape[2] == y.shape[2]
+            and x.shape[2] <= 1024 and x.shape[2] % 8 == 0 and not (torch.is_grad_enabled() and y.requires_grad))
+
+
 class ContextualLoss_forward(nn.Module):
     """Contextual loss between VGG feature maps (ContextualLoss.py:83-137)."""
 
@@ -60,6 +89,8 @@ class ContextualLoss_forward(nn.Module):
             X, Y = X - mu, Y - mu
         X = feature_normalize(X).view(b, c, -1)
         Y = feature_normalize(Y).view(b, c, -1)
+        if _ctx_rows_native(X, Y):
+            return -torch.log(torch.mean(_CtxRows.apply(X, Y.detach(), h), dim=1))
         d = 1 - torch.matmul(X.permute(0, 2, 1), Y)
         d_norm = d / (torch.min(d, dim=-1, keepdim=True)[0] + 1e-3)
         w = torch.exp((1 - d_norm) / h)

@@ -145,6 +145,28 @@ def corr_warp_bwd_ds(q16, k16, do16, rscale, v16, out, lse, cv, scale, want_pt):
     return ds[:, :, :nk], dst[:, :, :nq], (pt[:, :, :nq] if want_pt else None)
 
 
+def ctx_rows_fwd(S, h, eps=1e-3):
+    """S fp32 [B,N,N] (N <= 1024) -> cx [B,N] = max_j A_ij of the contextual loss (ContextualLoss.py:117-131)."""
+    _req(S, torch.float32, "S")
+    b, n, _ = S.shape
+    cx = torch.empty((b, n), dtype=torch.float32, device=S.device)
+    _lib.check(_lib.lib().cocos_ctx_rows_fwd(S.data_ptr(), cx.data_ptr(), b, n, float(h), float(eps), _stream()),
+               "cocos_ctx_rows_fwd")
+    return cx
+
+
+def ctx_rows_bwd(S, g, h, eps=1e-3):
+    """-> dS bf16 [B,N,N] (a view of a buffer whose row pitch is a multiple of 8) from g = dL/dcx [B,N]."""
+    _req(S, torch.float32, "S")
+    g = g.contiguous()
+    b, n, _ = S.shape
+    ld = round_up(n, 8)
+    ds = torch.empty((b, n, ld), dtype=torch.bfloat16, device=S.device)
+    _lib.check(_lib.lib().cocos_ctx_rows_bwd(S.data_ptr(), g.data_ptr(), ds.data_ptr(), b, n, ld, float(h), float(eps),
+                                             _stream()), "cocos_ctx_rows_bwd")
+    return ds[:, :, :n]
+
+
 def _is_cl(t):
     """channels_last 4-D tensor (and not simultaneously plain-contiguous)."""
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()

@@ -254,6 +254,15 @@ int cocos_spade_mod_nhwc_bwd(const void* dy, int dy_Cs, const void* x, int x_kin
                              int gb_kind, int gb_Cs, int gb_W, const float* mean, const float* rstd, void* dx,
                              int dx_Cs, int dx_acc, void* dgb, int dgb_Cs, int B, int C, int H, int W, int pad,
                              float slope, void* stream);
+/* Contextual loss (models/networks/ContextualLoss.py:93-137, called from pix2pix_model.py:196-203) on the correlation
+ * matrix S = Xhat^T Yhat, fp32 [B, N, N] with N <= 1024 (cocos_gemm_f16 on the normalised VGG features):
+ *   cx[b, i] = max_j A_ij,  A = row-normalised exp((1 - d / (min_j d + eps)) / h),  d = 1 - S
+ * (the loss of image b is -log(mean_i cx[b, i])), and its backward: dS (bf16, row pitch ldd >= N) from g = dL/dcx.
+ * One warp per row; d, d_norm, w, A of the reference never reach memory. */
+int cocos_ctx_rows_fwd(const float* S, float* cx, int B, int N, float h, float eps, void* stream);
+int cocos_ctx_rows_bwd(const float* S, const float* g, void* dS, int B, int N, int ldd, float h, float eps,
+                       void* stream);
+
 /* Spectral normalisation (torch.nn.utils.spectral_norm as normalization.py:30-31 applies it) of n layers at once:
  * `table` = n device-resident records of 8 x int64 {W fp32 [rows, cols] (weight_orig), u [rows], v [cols], rows, cols,
  * first block of the layer in phase A (128 columns per block), first block in phase B (8 rows per block), offset

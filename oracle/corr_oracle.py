@@ -296,3 +296,32 @@ def operand_prologue_backward(x, g, match_kernel=3):
     for t, (di, dj) in enumerate(taps):  # the fold: position n contributed x[., n + offset(t)]
         dx[:, :, half + di:half + di + h, half + dj:half + dj + w] += df[:, t]
     return dx[:, :, half:half + h, half:half + w]
+
+
+def contextual_rows(S, h=0.1, eps=1e-3):
+    """ContextualLoss.py:117-131 from the correlation matrix S [B,N,N]: cx[b,i] = max_j A_ij, written the way
+    cocos_ctx_rows_fwd computes it (the row maximum of A sits at the row minimum of d): 1 / sum_j exp(-a (d - m))."""
+    d = 1.0 - np.asarray(S, np.float64)
+    m = d.min(-1, keepdims=True)
+    a = 1.0 / (h * (m + eps))
+    return 1.0 / np.exp(-a * (d - m)).sum(-1)
+
+
+def contextual_rows_backward(S, g, h=0.1, eps=1e-3):
+    """dL/dS given g = dL/dcx [B,N]: the formula of cocos_ctx_rows_bwd (min routed to its first arg-min)."""
+    d = 1.0 - np.asarray(S, np.float64)
+    B, N, _ = d.shape
+    m = d.min(-1, keepdims=True)
+    arg = d.argmin(-1)
+    a = 1.0 / (h * (m + eps))
+    q = np.exp(-a * (d - m))
+    sumq = q.sum(-1, keepdims=True)
+    cx = 1.0 / sumq
+    c = np.asarray(g, np.float64)[..., None] * cx * cx * a
+    dd = c * q
+    onehot = np.zeros_like(d, dtype=bool)
+    np.put_along_axis(onehot, arg[..., None], True, -1)
+    sumqd = np.where(onehot, 0.0, q * (d - m)).sum(-1, keepdims=True)
+    at_min = c * ((sumq - 1.0) + sumqd / (m + eps))
+    dd = np.where(onehot, -at_min, dd)
+    return -dd

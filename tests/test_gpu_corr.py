@@ -464,3 +464,25 @@ def test_conv_native_forward_and_hybrid_backward(b, cin, cout, h, w, ks, pre_pad
     assert _rel(xin.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 4e-3
     assert _rel(wgt.grad.cpu().numpy(), wr.grad.cpu().numpy()) < 4e-3
     assert _rel(bias.grad.cpu().numpy(), br.grad.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("b,c,hw", [(2, 512, 16), (2, 256, 32)])
+def test_contextual_loss_kernels_vs_reference_expression(b, c, hw):
+    """ContextualLoss_forward on the tcgen05 GEMM + row kernels (cocos_ctx_rows_fwd / _bwd) against the reference's
+    expressions in fp64 (ContextualLoss.py:93-137): per-image loss and the gradient w.r.t. the source features."""
+    from cocosnet_b200.nets.losses import ContextualLoss_forward
+
+    class O:
+        PONO = True
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(b, c, hw, hw, generator=g).relu()
+    y = (0.5 * x + 0.8 * torch.randn(b, c, hw, hw, generator=g)).relu()
+    loss_fn = ContextualLoss_forward(O())
+    xg = x.cuda().requires_grad_(True)
+    got = loss_fn(xg, y.cuda())
+    got.sum().backward()
+    xr = x.double().requires_grad_(True)
+    want = loss_fn(xr, y.double())  # CPU: the reference's torch expressions
+    want.sum().backward()
+    assert _rel(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-3
+    assert _rel(xg.grad.cpu().numpy(), xr.grad.numpy()) < 2e-2

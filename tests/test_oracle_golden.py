@@ -91,3 +91,21 @@ def test_operand_prologue_backward_matches_autograd(mk):
     g_tap_major = g_ref_order.reshape(B, C, mk * mk, h * w).transpose(0, 2, 1, 3).reshape(B, C * mk * mk, h * w)
     got = oc.operand_prologue_backward(x, g_tap_major, mk)
     assert np.allclose(got, xt.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_contextual_rows_match_reference_expression_and_autograd():
+    """The per-row form of the contextual loss (cocos_ctx_rows_fwd / _bwd) == ContextualLoss.py:117-131 and autograd
+    through it, on a random correlation matrix."""
+    import torch
+    rng = np.random.default_rng(3)
+    S = rng.uniform(-0.4, 0.9, (2, 37, 37))
+    g = rng.standard_normal((2, 37))
+    St = torch.tensor(S, requires_grad=True)
+    d = 1 - St
+    d_norm = d / (torch.min(d, dim=-1, keepdim=True)[0] + 1e-3)
+    w = torch.exp((1 - d_norm) / 0.1)
+    A = w / torch.sum(w, dim=-1, keepdim=True)
+    cx = torch.max(A, dim=-1)[0]
+    (cx * torch.tensor(g)).sum().backward()
+    assert np.allclose(oc.contextual_rows(S), cx.detach().numpy(), rtol=1e-10)
+    assert np.allclose(oc.contextual_rows_backward(S, g), St.grad.numpy(), rtol=1e-8, atol=1e-12)
