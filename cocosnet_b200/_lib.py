@@ -50,6 +50,9 @@ SIGNATURES = {
                                 _c_int, _c_float, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _vp],
     "cocos_act_bwd_nhwc": [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int] + [_c_int] * 5 + [_c_float, _vp],
     "cocos_nhwc_pack": [_vp, _vp] + [_c_int] * 13 + [_vp],
+    "cocos_pair_loss_nhwc_fwd": [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_ll, _c_int, _c_float, _c_int, _vp, _vp],
+    "cocos_pair_loss_nhwc_bwd": [_vp, _c_int, _vp, _c_int, _vp, _c_int, _c_ll, _c_int, _c_float, _c_int, _vp, _vp, _c_int,
+                                 _c_int, _vp],
     "cocos_cast_op_bf16": [_vp, _c_int, _c_int, _vp, _c_int, _c_ll, _vp],
     "cocos_maxpool2_nhwc_fwd": [_vp, _vp] + [_c_int] * 4 + [_vp],
     "cocos_maxpool2_nhwc_bwd": [_vp, _vp, _vp] + [_c_int] * 4 + [_vp],

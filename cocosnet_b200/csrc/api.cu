@@ -276,6 +276,25 @@ int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs,
                           static_cast<cudaStream_t>(stream));
 }
 
+int cocos_pair_loss_nhwc_fwd(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                             float scale, int mode, float* out, void* stream) {
+  if (!x || !y || !out) {
+    set_error("cocos_pair_loss_nhwc_fwd: null pointer argument");
+    return -1;
+  }
+  return pair_loss_nhwc_fwd_launch(x, x_Cs, y, y_Cs, w, B, HW, C, scale, mode, out, static_cast<cudaStream_t>(stream));
+}
+
+int cocos_pair_loss_nhwc_bwd(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                             float scale, int mode, const float* g, void* dx, int dx_Cs, int acc, void* stream) {
+  if (!x || !y || !g || !dx) {
+    set_error("cocos_pair_loss_nhwc_bwd: null pointer argument");
+    return -1;
+  }
+  return pair_loss_nhwc_bwd_launch(x, x_Cs, y, y_Cs, w, B, HW, C, scale, mode, g, dx, dx_Cs, acc,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 int cocos_cast_op_bf16(const void* src, int src_Cs, int lo_off, void* dst, int dst_Cs, long long npix, void* stream) {
   if (!src || !dst) {
     set_error("cocos_cast_op_bf16: null pointer argument");

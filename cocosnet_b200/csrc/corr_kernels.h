@@ -100,6 +100,10 @@ int act_bwd_nhwc_launch(const void* dy, int dy_Cs, const void* y, int y_kind, in
                         int B, int C, int H, int W, int act, float slope, cudaStream_t stream);
 int nhwc_pack_launch(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
                      int Hs, int Ws, int H, int W, int f, int pad, cudaStream_t stream);
+int pair_loss_nhwc_fwd_launch(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                              float scale, int mode, float* out, cudaStream_t stream);
+int pair_loss_nhwc_bwd_launch(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                              float scale, int mode, const float* g, void* dx, int dx_Cs, int acc, cudaStream_t stream);
 int cast_op_bf16_launch(const void* src, int src_Cs, int lo_off, void* dst, int dst_Cs, long long npix,
                         cudaStream_t stream);
 int maxpool2_nhwc_fwd_launch(const void* x, void* y, int B, int Cs, int Ho, int Wo, cudaStream_t stream);

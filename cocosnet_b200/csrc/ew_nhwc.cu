@@ -557,6 +557,83 @@ act_bwd_nhwc_kernel(const void* __restrict__ dy, int dy_Cs, const void* __restri
   st4(dz, 2, static_cast<size_t>(pixl) * dz_Cs + c, d);
 }
 
+// ----------------------------------------------------------------------------------------------- feature losses
+// out[0] += scale * sum_b w[b] * sum_{pixels, c < C} |x - y|  (mode 0: criterionFeat / weighted_l1_loss,
+// pix2pix_model.py:240,253; util/util.py:36-40) or (x - y)^2 (mode 1: the perceptual MSE, pix2pix_model.py:256) over two
+// fp16 NHWC feature tensors -- the discriminator / VGG19 features never leave the 16-bit NHWC pipeline for their loss.
+// One block = 8 pixel lanes x 32 threads x 8 channels; block reduction, one atomic per block.
+__global__ void __launch_bounds__(256)
+pair_loss_nhwc_fwd_kernel(const uint16_t* __restrict__ x, int x_Cs, const uint16_t* __restrict__ y, int y_Cs,
+                          const float* __restrict__ w, int B, long long HW, int C8, float scale, int mode,
+                          float* __restrict__ out) {
+  __shared__ float red[8];
+  const long long total = static_cast<long long>(B) * HW * C8;
+  float acc = 0.f;
+  for (long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(idx % C8) * 8;
+    const long long pix = idx / C8;
+    const float wb = w ? w[pix / HW] : 1.0f;
+    const uint4 a = *reinterpret_cast<const uint4*>(x + pix * x_Cs + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(y + pix * y_Cs + c);
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+      const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+      s += mode ? (d0 * d0 + d1 * d1) : (fabsf(d0) + fabsf(d1));
+    }
+    acc = fmaf(wb, s, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(out, t * scale);
+  }
+}
+
+// dx (bf16) (+)= g[0] * scale * w[b] * sign(x - y)  (mode 0)  or  2 (x - y)  (mode 1)
+__global__ void __launch_bounds__(256)
+pair_loss_nhwc_bwd_kernel(const uint16_t* __restrict__ x, int x_Cs, const uint16_t* __restrict__ y, int y_Cs,
+                          const float* __restrict__ w, int B, long long HW, int C8, float scale, int mode,
+                          const float* __restrict__ g, uint16_t* __restrict__ dx, int dx_Cs, int acc) {
+  const long long total = static_cast<long long>(B) * HW * C8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8) * 8;
+  const long long pix = idx / C8;
+  const float k = __ldg(g) * scale * (w ? w[pix / HW] : 1.0f);
+  const uint4 a = *reinterpret_cast<const uint4*>(x + pix * x_Cs + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(y + pix * y_Cs + c);
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (acc) o = *reinterpret_cast<const uint4*>(dx + pix * dx_Cs + c);
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+    const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+    float g0, g1;
+    if (mode) {
+      g0 = 2.f * k * d0; g1 = 2.f * k * d1;
+    } else {
+      g0 = d0 > 0.f ? k : (d0 < 0.f ? -k : 0.f);
+      g1 = d1 > 0.f ? k : (d1 < 0.f ? -k : 0.f);
+    }
+    float2 old = make_float2(0.f, 0.f);
+    if (acc) old = __bfloat1622float2(ob[i]);
+    ob[i] = __floats2bfloat162_rn(old.x + g0, old.y + g1);
+  }
+  *reinterpret_cast<uint4*>(dx + pix * dx_Cs + c) = o;
+}
+
 // ----------------------------------------------------------------------------------------------- fp16 -> bf16 operand
 // The backward-weights GEMM multiplies dY (bf16: gradients need the fp32 exponent range) with the activation X the
 // forward saved (fp16 [hi | lo]); tcgen05 cannot mix fp16 x bf16 operands, and converting X inside the GEMM kernel
@@ -993,6 +1070,36 @@ int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
   nhwc_unpack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, kind, Cs, c_lo, C, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f,
                                                         acc);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pair_loss_nhwc_fwd_launch(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                              float scale, int mode, float* out, cudaStream_t stream) {
+  if (B <= 0 || HW <= 0 || C <= 0 || (C % 8) || (x_Cs % 8) || (y_Cs % 8) || x_Cs < C || y_Cs < C || mode < 0 || mode > 1) {
+    set_error("pair_loss_nhwc_fwd: bad arguments (B=%d HW=%lld C=%d x_Cs=%d y_Cs=%d)", B, HW, C, x_Cs, y_Cs);
+    return -1;
+  }
+  const long long total = static_cast<long long>(B) * HW * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pair_loss_nhwc_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(x), x_Cs, static_cast<const uint16_t*>(y), y_Cs, w, B, HW, C / 8, scale, mode, out);
+  COCOS_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pair_loss_nhwc_bwd_launch(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                              float scale, int mode, const float* g, void* dx, int dx_Cs, int acc, cudaStream_t stream) {
+  if (B <= 0 || HW <= 0 || C <= 0 || (C % 8) || (x_Cs % 8) || (y_Cs % 8) || (dx_Cs % 8) || x_Cs < C || y_Cs < C ||
+      dx_Cs < C || mode < 0 || mode > 1) {
+    set_error("pair_loss_nhwc_bwd: bad arguments (B=%d HW=%lld C=%d)", B, HW, C);
+    return -1;
+  }
+  const long long total = static_cast<long long>(B) * HW * (C / 8);
+  pair_loss_nhwc_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(x), x_Cs, static_cast<const uint16_t*>(y), y_Cs, w, B, HW, C / 8, scale, mode, g,
+      static_cast<uint16_t*>(dx), dx_Cs, acc);
   COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -412,9 +412,11 @@ def discriminator_supported(net, sem, img):
     return True
 
 
-def _d_chain(tp, ps, layers, x, emit_all, emit_last=False, first_w=None):
+def _d_chain(tp, ps, layers, x, emit_all, emit_last=False, first_w=None, collect=None, versus=None, loss=None):
     """Conv (+ InstanceNorm) (+ LeakyReLU) layers on the tape -> fp32 NCHW outputs: every layer's (emit_all), or only
-    the last one's (emit_last), plus the prediction when the chain ends with it."""
+    the last one's (emit_last), plus the prediction when the chain ends with it.  collect: list that receives the
+    feature NTs (a tape-free pass over the real images); versus + loss = (out, slot, scale_of(nt)): the feature-matching
+    loss against those NTs is accumulated on the NHWC features themselves (pix2pix_model.py:233-242)."""
     outs = []
     for i, (_, conv, norm, slope) in enumerate(layers):
         W = first_w if (i == 0 and first_w is not None) else ps.w(conv)
@@ -427,25 +429,41 @@ def _d_chain(tp, ps, layers, x, emit_all, emit_last=False, first_w=None):
         else:
             r = T.conv(tp, x, W, ps.b(conv), stride=stride, padding=1, out_kind=F16)
             x, _ = T.inst_act(tp, r, slope=slope, eps=norm.eps, out_kind=F16)
+        if collect is not None:
+            collect.append(x.v)
+        if versus is not None:
+            out, slot, scale_of = loss
+            T.pair_loss(tp, x, versus[i], out, slot, scale_of(x.v))
         if emit_all or (emit_last and i == len(layers) - 1):
             outs.append(T.unpack_out(tp, x))
     return outs
 
 
+def fused_losses():
+    """Feature-matching / VGG / perceptual losses accumulated by kernels on the fp16 NHWC features
+    (COCOS_FUSED_LOSSES=0: features unpacked to fp32 NCHW and compared by torch ops, for A/B runs)."""
+    import os
+    return os.environ.get("COCOS_FUSED_LOSSES", "1") != "0"
+
+
 def discriminator_forward(net, sem, fake, real, need_feats=True):
     """MultiscaleDiscriminator.forward (discriminator.py:56-69) on cat([sem | fake], [sem | real]) -- the batch
-    pix2pix_model.py:299-304 builds -- without building it: returns (pred_fake, pred_real) as divide_pred does
-    (pix2pix_model.py:320-333).  The label map and the two images are packed straight into the fp16 NHWC input of the
-    first 4x4 convolution (image channels first, so every channel window is 16-byte aligned; the filter's input
-    channels are permuted to match).  In the generator step (fake carries a gradient) the fake half is recorded and the
-    real half runs without a tape; in the discriminator step both halves are one batch."""
+    pix2pix_model.py:299-304 builds -- without building it: returns (pred_fake, pred_real, feat_loss) with the
+    predictions as divide_pred arranges them (pix2pix_model.py:320-333).  The label map and the two images are packed
+    straight into the fp16 NHWC input of the first 4x4 convolution (image channels first, so every channel window is
+    16-byte aligned; the filter's input channels are permuted to match).  In the generator step (fake carries a
+    gradient) the real half runs first without a tape and keeps its features as NHWC tensors, the fake half is recorded
+    and accumulates the feature-matching loss against them where they live (feat_loss, pix2pix_model.py:233-242; the
+    lists then hold the predictions only); in the discriminator step both halves are one batch and no feature is kept."""
     opt = net.opt
-    # the intermediate features only feed the feature-matching loss of the generator step (pix2pix_model.py:233-242)
     keep_feats = need_feats and not opt.no_ganFeat_loss
     B, ns, ni = sem.shape[0], sem.shape[1], fake.shape[1]
     need_dx = fake.requires_grad and torch.is_grad_enabled()
-    halves = [(fake, True), (real, False)] if need_dx else [(None, False)]
-    pred = [[] for _ in halves]
+    fuse = need_dx and keep_feats and fused_losses()
+    unpack_feats = keep_feats and not fuse
+    num_D = len(list(net.named_children()))
+    pred = [[], []] if need_dx else [[]]
+    feat_loss = None
     sem_s, fake_s, real_s = sem, fake, real
     pool = lambda t: F.avg_pool2d(t, kernel_size=3, stride=2, padding=[1, 1], count_include_pad=False)  # noqa: E731
     for si, (_, D) in enumerate(net.named_children()):
@@ -461,8 +479,16 @@ def discriminator_forward(net, sem, fake, real, need_feats=True):
         w0 = torch.cat((c0.weight[:, ns:ns + ni], c0.weight.new_zeros((c0.out_channels, 8 - ni, 4, 4)), c0.weight[:, :ns]), 1)
         ps.tensor("w0", w0)
         H, Wd = sem_s.shape[2:]
+        real_nts = []
+        scale_of = lambda nt: opt.lambda_feat / num_D / float(nt.B * nt.H * nt.W * nt.C)  # noqa: E731  (L1Loss mean)
 
-        def stage_a(images, grads, record):
+        def run(body, inputs, record):
+            if record:
+                return list(T.run(body, inputs, ps.tensors))
+            with torch.no_grad():
+                return list(T.run(body, inputs, ps.tensors))
+
+        def stage_a(images, grads, record, collect=None, versus=None):
             nb = B * len(images)
 
             def body(tp, ins, params):
@@ -472,40 +498,56 @@ def discriminator_forward(net, sem, fake, real, need_feats=True):
                     parts.append((1 + k, ins[1 + k], k * B, 0, 8, g))
                     parts.append((0, ins[0], k * B, 8, 0, False))
                 x = T.pack_parts(tp, nb, H, Wd, 8 + ns, parts)
-                return _d_chain(tp, ps, layers[:cut], x, keep_feats, emit_last=cut < len(layers), first_w=ps.t("w0"))
-            if record:
-                return list(T.run(body, [sem_s] + images, ps.tensors))
-            with torch.no_grad():
-                return list(T.run(body, [sem_s] + images, ps.tensors))
+                outs, loss = [], None
+                if versus is not None:
+                    out, slot = T.loss_out(tp, ins[0].device)
+                    outs, loss = [out], (out, slot, scale_of)
+                return outs + _d_chain(tp, ps, layers[:cut], x, unpack_feats, emit_last=cut < len(layers),
+                                       first_w=ps.t("w0"), collect=collect, versus=versus, loss=loss)
+            return run(body, [sem_s] + images, record)
 
-        def stage_b(x3, record):
+        def stage_b(x3, record, collect=None, versus=None):
             def body(tp, ins, params):
                 ps.bind(params)
                 x = T.pack_in(tp, 0, ins[0], F16, grad_ch=(0, ins[0].shape[1]))
-                return _d_chain(tp, ps, layers[cut:], x, keep_feats)
-            if record:
-                return list(T.run(body, [x3], ps.tensors))
-            with torch.no_grad():
-                return list(T.run(body, [x3], ps.tensors))
+                outs, loss = [], None
+                if versus is not None:
+                    out, slot = T.loss_out(tp, ins[0].device)
+                    outs, loss = [out], (out, slot, scale_of)
+                return outs + _d_chain(tp, ps, layers[cut:], x, unpack_feats, collect=collect, versus=versus, loss=loss)
+            return run(body, [x3], record)
 
-        if need_dx:
-            outs = [stage_a([fake_s], [True], True), stage_a([real_s], [False], False)]
+        if need_dx:  # the real half first: its features are the targets of the fake half's loss
+            o_real = stage_a([real_s], [False], False, collect=real_nts if fuse else None)
+            o_fake = stage_a([fake_s], [True], True, versus=real_nts[:cut] if fuse else None)
+            outs = [o_fake, o_real]
         else:
             outs = [stage_a([fake_s, real_s], [False, False], True)]
+        losses = []
+        if fuse:
+            losses.append(outs[0][0])
+            outs[0] = outs[0][1:]
         if cut < len(layers):
             # the SAGAN block in front of model3 (discriminator.py:146-147): ONE call on both halves, so that its
             # spectral-norm power iterations advance once per forward like the reference's
             x3 = D.attn(torch.cat([o[-1] for o in outs], 0) if need_dx else outs[0][-1])
             if need_dx:
-                tails = [stage_b(x3[:B], True), stage_b(x3[B:].detach(), False)]
+                t_real = stage_b(x3[B:].detach(), False, collect=real_nts if fuse else None)
+                t_fake = stage_b(x3[:B], True, versus=real_nts[cut:] if fuse else None)
+                if fuse:
+                    losses.append(t_fake[0])
+                    t_fake = t_fake[1:]
+                tails = [t_fake, t_real]
             else:
                 tails = [stage_b(x3, True)]
-            outs = [(a if keep_feats else []) + t for a, t in zip(outs, tails)]
+            outs = [(a if unpack_feats else []) + t for a, t in zip(outs, tails)]
         for k, o in enumerate(outs):
             pred[k].append(o)
+        for t in losses:
+            feat_loss = t if feat_loss is None else feat_loss + t
     if need_dx:
-        return pred[0], pred[1]
-    return ([[t[:B] for t in o] for o in pred[0]], [[t[B:] for t in o] for o in pred[0]])
+        return pred[0], pred[1], feat_loss
+    return ([[t[:B] for t in o] for o in pred[0]], [[t[B:] for t in o] for o in pred[0]], None)
 
 
 # ------------------------------------------------------------------------------------------------ VGG19 features
@@ -514,31 +556,86 @@ def vgg_supported(net, x):
         and isinstance(net.pool1, nn.MaxPool2d)
 
 
-def vgg_forward(net, x, out_keys, cfg):
-    """VGG19_feature_color_torchversion.forward (correspondence.py:108-146) after the colour preprocessing: conv +
-    ReLU in one tap-convolution launch each, 2x2 max pooling on fp16 NHWC, the requested relu outputs unpacked to
-    fp32 NCHW for the losses.  cfg: [(attribute name, Cin, Cout)] in network order."""
+def _vgg_chain(tp, ps, net, names, h, out_keys, on_feature):
+    """conv + ReLU (+ 2x2 max pooling) chain; on_feature(key, Var) for every relu output in out_keys."""
+    done = set()
+    for n in names:
+        blk, idx = int(n[4]), int(n[6])
+        c = getattr(net, n)
+        h = T.conv(tp, h, ps.w(c), ps.b(c), padding=1, act=ACT_RELU, out_kind=F16)
+        key = "r%d%d" % (blk, idx)
+        if key in out_keys:
+            on_feature(key, h)
+            done.add(key)
+        if all(k in done for k in out_keys):
+            break
+        if idx == (2 if blk <= 2 else 4):
+            h = T.maxpool(tp, h)
+
+
+def _vgg_params(net, out_keys, cfg):
     last = max(int(k[1]) for k in out_keys)
     names = [n for n, _, _ in cfg if int(n[4]) <= last]
     ps = ParamSet()
     for n in names:
         ps.conv(getattr(net, n))
+    return ps, names
+
+
+def vgg_forward(net, x, out_keys, cfg):
+    """VGG19_feature_color_torchversion.forward (correspondence.py:108-146) after the colour preprocessing: conv +
+    ReLU in one tap-convolution launch each, 2x2 max pooling on fp16 NHWC, the requested relu outputs unpacked to
+    fp32 NCHW for the losses.  cfg: [(attribute name, Cin, Cout)] in network order."""
+    ps, names = _vgg_params(net, out_keys, cfg)
     need = x.requires_grad and torch.is_grad_enabled()
 
     def body(tp, ins, params):
         ps.bind(params)
         h = T.pack_in(tp, 0, ins[0], F16, grad_ch=(0, ins[0].shape[1]) if need else None)
         outs = {}
-        for n in names:
-            blk, idx = int(n[4]), int(n[6])
-            c = getattr(net, n)
-            h = T.conv(tp, h, ps.w(c), ps.b(c), padding=1, act=ACT_RELU, out_kind=F16)
-            key = "r%d%d" % (blk, idx)
-            if key in out_keys:
-                outs[key] = T.unpack_out(tp, h)
-            if all(k in outs for k in out_keys):
-                break
-            if idx == (2 if blk <= 2 else 4):
-                h = T.maxpool(tp, h)
+        _vgg_chain(tp, ps, net, names, h, out_keys, lambda key, v: outs.__setitem__(key, T.unpack_out(tp, v)))
         return [outs[k] for k in out_keys]
     return list(T.run(body, [x], ps.tensors))
+
+
+def vgg_features_nt(net, x, out_keys, cfg):
+    """The relu outputs as fp16 NHWC tensors (no tape, no fp32 copies): the targets of vgg_forward_losses."""
+    ps, names = _vgg_params(net, out_keys, cfg)
+    with torch.no_grad():
+        tp = T.Tape(False)
+        ps.bind([T.Param(t.detach(), False) for t in ps.tensors])
+        h = T.pack_in(tp, 0, x.detach(), F16)
+        nts = {}
+        _vgg_chain(tp, ps, net, names, h, out_keys, lambda key, v: nts.__setitem__(key, v.v))
+    return nts
+
+
+def vgg_forward_losses(net, x, cfg, target_nts, l1_terms, sample_w, mse_terms, out_keys):
+    """One recorded VGG19 pass over the generated image that (a) accumulates, on the NHWC features, the weighted-L1
+    feature loss sum_k l1_terms[k] * mean(|f_k - t_k| * sample_w) (pix2pix_model.py:250-254; util/util.py:36-40) and the
+    MSE terms sum_k mse_terms[k] * mean((f_k - t_k)^2) (pix2pix_model.py:255-256) against target_nts (vgg_features_nt of
+    the real image), and (b) unpacks only out_keys (what the contextual loss reads) to fp32 NCHW.
+    Returns ([features of out_keys], l1_loss [1], mse_loss [1])."""
+    keys = sorted(set(out_keys) | set(l1_terms) | set(mse_terms))
+    ps, names = _vgg_params(net, keys, cfg)
+    need = x.requires_grad and torch.is_grad_enabled()
+
+    def body(tp, ins, params):
+        ps.bind(params)
+        h = T.pack_in(tp, 0, ins[0], F16, grad_ch=(0, ins[0].shape[1]) if need else None)
+        l1, l1_slot = T.loss_out(tp, ins[0].device)
+        mse, mse_slot = T.loss_out(tp, ins[0].device)
+        feats = {}
+
+        def on_feature(key, v):
+            n = float(v.v.B * v.v.H * v.v.W * v.v.C)
+            if key in l1_terms:
+                T.pair_loss(tp, v, target_nts[key], l1, l1_slot, l1_terms[key] / n, mode=0, w=ins[1])
+            if key in mse_terms:
+                T.pair_loss(tp, v, target_nts[key], mse, mse_slot, mse_terms[key] / n, mode=1)
+            if key in out_keys:
+                feats[key] = v
+        _vgg_chain(tp, ps, net, names, h, keys, on_feature)
+        return [l1, mse] + [T.unpack_out(tp, feats[k]) for k in out_keys]
+    outs = list(T.run(body, [x, sample_w.reshape(-1).contiguous()], ps.tensors))
+    return outs[2:], outs[0], outs[1]

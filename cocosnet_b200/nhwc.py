@@ -264,6 +264,16 @@ class NativeBackend:
         _lib.check(self.lib.cocos_nhwc_pack(src.data_ptr(), dst.t.data_ptr(), dst.kind, b, C, dst.Cs, dst.lo, c_lo, c_span,
                                             hs, ws, dst.H, dst.W, f, dst.pad, _stream()), "cocos_nhwc_pack")
 
+    def pair_loss_fwd(self, x, y, w, scale, mode, out):
+        _lib.check(self.lib.cocos_pair_loss_nhwc_fwd(x.t.data_ptr(), x.Cs, y.t.data_ptr(), y.Cs, _p(w), x.B, x.H * x.W,
+                                                     x.C, float(scale), int(mode), out.data_ptr(), _stream()),
+                   "cocos_pair_loss_nhwc_fwd")
+
+    def pair_loss_bwd(self, x, y, w, scale, mode, g, dx, acc):
+        _lib.check(self.lib.cocos_pair_loss_nhwc_bwd(x.t.data_ptr(), x.Cs, y.t.data_ptr(), y.Cs, _p(w), x.B, x.H * x.W,
+                                                     x.C, float(scale), int(mode), g.data_ptr(), dx.t.data_ptr(), dx.Cs,
+                                                     int(acc), _stream()), "cocos_pair_loss_nhwc_bwd")
+
     def cast_bf16(self, x, dst):
         _lib.check(self.lib.cocos_cast_op_bf16(x.t.data_ptr(), x.Cs, x.lo, dst.t.data_ptr(), dst.Cs,
                                                x.t.numel() // x.Cs, _stream()), "cocos_cast_op_bf16")
@@ -338,6 +348,22 @@ def pack_into(src, dst, b_lo=0, c_lo=0, c_span=0, f=1):
 
 def batch_view(x, lo, hi):
     return NT(x.t[lo:hi], x.kind, x.C, x.pad, x.lo)
+
+
+def pair_loss(x, y, out, scale, mode=0, w=None):
+    """out[0] += scale * sum_b w[b] sum |x - y| (mode 0) or (x - y)^2 (mode 1); x, y fp16 NTs without halo."""
+    assert x.kind == F16 and y.kind == F16 and x.pad == 0 and y.pad == 0 and x.lo == 0 and y.lo == 0
+    assert x.C == y.C and x.C % 8 == 0 and tuple(x.t.shape[:3]) == tuple(y.t.shape[:3])
+    backend().pair_loss_fwd(x, y, w, scale, mode, out)
+
+
+def pair_loss_bwd(x, y, g, scale, mode=0, w=None, dx=None):
+    """-> dx bf16 NT (accumulated into `dx` when given): g[0] * scale * w[b] * d/dx of the pair loss."""
+    acc = dx is not None
+    if dx is None:
+        dx = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=x.Cs != x.C)
+    backend().pair_loss_bwd(x, y, w, scale, mode, g, dx, acc)
+    return dx
 
 
 def as_bf16(x):

@@ -193,9 +193,11 @@ class Pix2PixModel(torch.nn.Module):
             G_losses["G_warp_self"] = torch.mean(F.l1_loss(gen["warp_out"], real_image, reduction="none") * sw) \
                 * opt.warp_self_w
 
-        pred_fake, pred_real, _, _, _ = self.discriminate(input_semantics, gen["fake_image"], real_image)
+        pred_fake, pred_real, extra, _, _ = self.discriminate(input_semantics, gen["fake_image"], real_image)
         G_losses["GAN"] = self.criterionGAN(pred_fake, True, for_discriminator=False) * opt.weight_gan
-        if not opt.no_ganFeat_loss:
+        if not opt.no_ganFeat_loss and isinstance(extra, dict) and extra.get("GAN_Feat") is not None:
+            G_losses["GAN_Feat"] = extra["GAN_Feat"]
+        elif not opt.no_ganFeat_loss:
             num_D = len(pred_fake)
             feat = torch.zeros(1, device=real_image.device)
             for i in range(num_D):
@@ -204,14 +206,30 @@ class Pix2PixModel(torch.nn.Module):
             G_losses["GAN_Feat"] = feat
 
         keys = ["r12", "r22", "r32", "r42", "r52"]
-        fake_features = self.vggnet_fix(gen["fake_image"], keys, preprocess=True)
         sw = self._sample_weights(self_ref)
-        loss = 0
-        for wgt, ff, rf in zip([1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0], fake_features, gen["real_features"]):
-            loss = loss + wgt * util.weighted_l1_loss(ff, rf.detach(), sw)
-        G_losses["fm"] = loss * opt.lambda_vgg * opt.fm_ratio
-        G_losses["perc"] = util.mse_loss(fake_features[self.perceptual_layer],
-                                         gen["real_features"][self.perceptual_layer].detach()) * opt.weight_perceptual
+        fm_w = dict(zip(keys, [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]))
+        if gen.get("real_features_nt") is not None:
+            # one recorded VGG19 pass: the feature (weighted L1) and perceptual (MSE) losses are accumulated on the fp16
+            # NHWC features against the real image's, only what the contextual loss reads is unpacked
+            from .nets import fast as _fast
+            from .nets.correspondence import _VGG_CFG
+            from .util import vgg_preprocess
+            ctx_keys = keys[-4:] if opt.use_22ctx else keys[-3:]
+            x = vgg_preprocess(gen["fake_image"], vgg_normal_correct=self.vggnet_fix.vgg_normal_correct)
+            ctx_feats, l1, mse = _fast.vgg_forward_losses(
+                self.vggnet_fix, x, _VGG_CFG, gen["real_features_nt"],
+                {k: w * opt.lambda_vgg * opt.fm_ratio for k, w in fm_w.items()}, sw,
+                {keys[self.perceptual_layer]: opt.weight_perceptual}, ctx_keys)
+            G_losses["fm"], G_losses["perc"] = l1.reshape(()), mse.reshape(())
+            fake_features = [None] * (len(keys) - len(ctx_keys)) + list(ctx_feats)
+        else:
+            fake_features = self.vggnet_fix(gen["fake_image"], keys, preprocess=True)
+            loss = 0
+            for k, ff, rf in zip(keys, fake_features, gen["real_features"]):
+                loss = loss + fm_w[k] * util.weighted_l1_loss(ff, rf.detach(), sw)
+            G_losses["fm"] = loss * opt.lambda_vgg * opt.fm_ratio
+            G_losses["perc"] = util.mse_loss(fake_features[self.perceptual_layer],
+                                             gen["real_features"][self.perceptual_layer].detach()) * opt.weight_perceptual
         G_losses["contextual"] = self.get_ctx_loss(fake_features, gen["ref_features"]) * opt.lambda_vgg * opt.ctx_w
 
         if opt.warp_mask_losstype != "none":  # pix2pix_model.py:261-276
@@ -245,9 +263,20 @@ class Pix2PixModel(torch.nn.Module):
 
     def generate_fake(self, input_semantics, real_image, ref_semantics=None, ref_image=None, self_ref=None):
         keys = ["r12", "r22", "r32", "r42", "r52"]
-        gen = {"ref_features": self.vggnet_fix(ref_image, keys, preprocess=True)}
+        # only the layers the contextual loss reads (pix2pix_model.py:196-203 indexes them from the end)
+        ctx_keys = keys[-4:] if self.opt.use_22ctx else keys[-3:]
+        gen = {"ref_features": self.vggnet_fix(ref_image, ctx_keys, preprocess=True)}
         coor_out = self.net["netCorr"](ref_image, real_image, input_semantics, ref_semantics, alpha=self.alpha)
-        gen["real_features"] = self.vggnet_fix(real_image, keys, preprocess=True)
+        from .nets import fast as _fast
+        if _fast.fused_losses() and _fast.vgg_supported(self.vggnet_fix, real_image):
+            # the real image's VGG features stay fp16 NHWC: targets of the fused feature / perceptual losses
+            from .nets.correspondence import _VGG_CFG
+            from .util import vgg_preprocess
+            gen["real_features_nt"] = _fast.vgg_features_nt(
+                self.vggnet_fix, vgg_preprocess(real_image, vgg_normal_correct=self.vggnet_fix.vgg_normal_correct), keys,
+                _VGG_CFG)
+        else:
+            gen["real_features"] = self.vggnet_fix(real_image, keys, preprocess=True)
         gen["fake_image"] = self.net["netG"](input_semantics, warp_out=self._cbn_in(coor_out, input_semantics))
         return {**gen, **coor_out}
 
@@ -260,9 +289,10 @@ class Pix2PixModel(torch.nn.Module):
         from .nets import fast as _fast
         if _fast.discriminator_supported(self.net["netD"], input_semantics, real_image):
             # [semantics | image] pairs packed straight into the fp16 NHWC input of the PatchGANs (no fp32 concat)
-            pred_fake, pred_real = _fast.discriminator_forward(self.net["netD"], input_semantics, fake_image, real_image,
-                                                               need_feats=need_feats)
-            return pred_fake, pred_real, [], None, None
+            pred_fake, pred_real, feat_loss = _fast.discriminator_forward(self.net["netD"], input_semantics, fake_image,
+                                                                          real_image, need_feats=need_feats)
+            # feat_loss: the feature-matching loss already accumulated on the NHWC features (generator step)
+            return pred_fake, pred_real, {"GAN_Feat": feat_loss}, None, None
         fake_and_real = torch.cat([torch.cat([input_semantics, fake_image], dim=1),
                                    torch.cat([input_semantics, real_image], dim=1)], dim=0)
         d_out, seg, cam_logit = self.net["netD"](fake_and_real)

@@ -120,6 +120,30 @@ def pack_parts(tp, B, H, W, C, parts, kind=F16, pad=0):
     return v
 
 
+def loss_out(tp, device):
+    """A scalar Function output the pair-loss kernels accumulate into; returns (tensor [1], slot).  The slot receives the
+    upstream gradient of that scalar when the backward starts."""
+    out = torch.zeros((1,), dtype=torch.float32, device=device)
+    slot = {"g": None}
+
+    def seed(g):
+        slot["g"] = g.reshape(1).contiguous()
+    tp.exits.append(seed)
+    return out, slot
+
+
+def pair_loss(tp, x, y_nt, out, slot, scale, mode=0, w=None):
+    """out[0] += scale * sum_b w[b] * sum |x - y| (mode 0) / (x - y)^2 (mode 1): the feature-matching, VGG and
+    perceptual losses (pix2pix_model.py:233-256) on the fp16 NHWC features themselves."""
+    nhwc.pair_loss(x.v, y_nt, out, scale, mode, w)
+
+    def bwd():
+        if slot["g"] is None or not x.need:
+            return
+        x.g = nhwc.pair_loss_bwd(x.v, y_nt, slot["g"], scale, mode, w, dx=x.g)
+    tp.add(bwd)
+
+
 def unpack_out(tp, x):
     """Var -> fp32 NCHW Function output."""
     out = nhwc.unpack(x.v)

@@ -314,6 +314,14 @@ int cocos_act_bwd_nhwc(const void* dy, int dy_Cs, const void* y, int y_kind, int
  * image), 1) of pix2pix_model.py:301-302 without the concatenated tensor. */
 int cocos_nhwc_pack(const float* src, void* dst, int kind, int B, int C, int Cs, int lo_off, int c_lo, int c_span,
                     int Hs, int Ws, int H, int W, int f, int pad, void* stream);
+/* Feature losses on fp16 NHWC tensors x, y [B, HW, Cs] (C % 8 == 0): out[0] += scale * sum_b w[b] * sum |x - y| (mode 0:
+ * criterionFeat / weighted_l1_loss, pix2pix_model.py:240,253, util/util.py:36-40; w may be NULL) or (x - y)^2 (mode 1,
+ * pix2pix_model.py:256), and the gradient w.r.t. x: dx (bf16, added to its content if acc) = g[0] * scale * w[b] *
+ * d/dx.  The discriminator / VGG19 features are compared where they live instead of as fp32 NCHW copies. */
+int cocos_pair_loss_nhwc_fwd(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                             float scale, int mode, float* out, void* stream);
+int cocos_pair_loss_nhwc_bwd(const void* x, int x_Cs, const void* y, int y_Cs, const float* w, int B, long long HW, int C,
+                             float scale, int mode, const float* g, void* dx, int dx_Cs, int acc, void* stream);
 /* fp16 operand [npix, src_Cs] (hi at channels [0, dst_Cs), optional lo term at lo_off) -> bf16 [npix, dst_Cs] =
  * bf16(hi + lo): the X operand of cocos_tapwgrad (the weight-gradient half of autograd's convolution_backward),
  * converted once per tensor instead of inside the GEMM.  Channel counts are multiples of 8. */

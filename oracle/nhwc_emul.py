@@ -320,6 +320,19 @@ class EmulBackend:
         if dst.lo:
             dst.t[..., dst.lo + c_lo:dst.lo + c_lo + span] = self._pad_reflect(full - hi, dst.pad).to(dst.t.dtype)
 
+    def pair_loss_fwd(self, x, y, w, scale, mode, out):
+        d = x.t.float()[..., :x.C] - y.t.float()[..., :x.C]
+        per = (d * d if mode else d.abs()).sum((1, 2, 3))
+        out += scale * (per * (w.float() if w is not None else 1.0)).sum()
+
+    def pair_loss_bwd(self, x, y, w, scale, mode, g, dx, acc):
+        d = x.t.float()[..., :x.C] - y.t.float()[..., :x.C]
+        k = g.float().reshape(()) * scale * (w.float()[:, None, None, None] if w is not None else 1.0)
+        grad = k * (2 * d if mode else torch.sign(d))
+        if acc:
+            grad = grad + dx.t.float()[..., :x.C]
+        dx.t[..., :x.C] = grad.to(dx.t.dtype)
+
     def cast_bf16(self, x, dst):
         cs = dst.t.shape[3]
         v = x.t.float()[..., :cs] + (x.t.float()[..., x.lo:x.lo + cs] if x.lo else 0)
