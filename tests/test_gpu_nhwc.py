@@ -395,3 +395,32 @@ def test_inst_act_nhwc_spade_modulation(C, H, W, B, pad, batch, const, xk):
         z = torch.nn.functional.pad(z, (pad,) * 4, mode="reflect")
     w0 = want[0].float()
     assert rel(w0[..., :C] + w0[..., w0.shape[3] // 2:][..., :C], z.permute(0, 2, 3, 1)) < 1e-3
+
+
+@pytest.mark.parametrize("mode,with_w", [(0, True), (0, False), (1, False)])
+def test_pair_loss_nhwc(mode, with_w):
+    """Feature-matching / VGG L1 / perceptual MSE accumulated on fp16 NHWC features, forward and backward."""
+    g = torch.Generator().manual_seed(5 + mode)
+    B, C, H, W = 3, 64, 24, 20
+    x, y = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    w = torch.tensor([0.5, 0.0, 0.5]) if with_w else None
+
+    def fn(dev):
+        xn, yn = nhwc.pack(x.to(dev), nhwc.F16), nhwc.pack(y.to(dev), nhwc.F16)
+        out = torch.zeros(1, device=dev)
+        wd = None if w is None else w.to(dev)
+        nhwc.pair_loss(xn, yn, out, 0.37, mode, wd)
+        nhwc.pair_loss(xn, yn, out, 0.37, mode, wd)  # accumulates
+        gsc = torch.full((1,), 2.0, device=dev)
+        dx = nhwc.pair_loss_bwd(xn, yn, gsc, 0.37, mode, wd)
+        dx = nhwc.pair_loss_bwd(xn, yn, gsc, 0.37, mode, wd, dx=dx)
+        return out, dx.t
+
+    got, want = both(fn)
+    assert rel(got[0], want[0]) < 1e-4
+    assert rel(got[1], want[1]) < 1e-2
+    xh, yh = x.half().float(), y.half().float()
+    d = xh - yh
+    per = (d * d if mode else d.abs()).sum((1, 2, 3))
+    ref = 2 * 0.37 * (per * (w if w is not None else 1.0)).sum()
+    assert abs(float(got[0]) - float(ref)) < 1e-4 * abs(float(ref))
