@@ -822,6 +822,44 @@ nhwc_unpack_kernel(const void* __restrict__ src, int kind, int Cs, int c_lo, int
   }
 }
 
+// Fast path of nhwc_unpack for 16-bit sources without halo (the common case: features handed to torch): a block moves
+// 32 pixels x 64 channels; 16-byte loads along the channels, 128-byte stores along the pixels.
+__global__ void __launch_bounds__(256)
+nhwc_unpack16_kernel(const uint16_t* __restrict__ src, int bf16, int Cs, int c_lo, int C, int HW, float* __restrict__ dst,
+                     int Cd, int cd_lo, int acc) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  {
+    const int cv = (threadIdx.x & 7) * 8, pix = p0 + (threadIdx.x >> 3);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (pix < HW && c0 + cv < C) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * HW + pix) * Cs + c_lo + c0 + cv);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f;
+        if (bf16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[cv + i][threadIdx.x >> 3] = v[i];
+  }
+  __syncthreads();
+  const int pix = p0 + (threadIdx.x & 31);
+  if (pix >= HW) return;
+#pragma unroll
+  for (int k = 0; k < 64; k += 8) {
+    const int c = c0 + k + (threadIdx.x >> 5);
+    if (c < C) {
+      float* d = dst + (static_cast<size_t>(b) * Cd + cd_lo + c) * HW + pix;
+      const float v = tile[k + (threadIdx.x >> 5)][threadIdx.x & 31];
+      *d = acc ? *d + v : v;
+    }
+  }
+}
+
 // db[c] += sum over rows of a 16-bit / fp32 [rows, Cs] matrix (out zeroed by the launcher); grid (row chunks, C/128)
 __global__ void __launch_bounds__(256)
 colsum_nhwc_kernel(const void* __restrict__ x, int kind, int Cs, int C, long long rows, int rows_per_block,
@@ -1066,6 +1104,15 @@ int nhwc_unpack_launch(const void* src, int kind, int Cs, int c_lo, int C, int B
       (H - 1) * f >= Hd || (W - 1) * f >= Wd || pad < 0 || pad > 1 || kind < 1 || kind > 3) {
     set_error("nhwc_unpack: bad arguments (B=%d C=%d Cs=%d H=%d W=%d f=%d pad=%d)", B, C, Cs, H, W, f, pad);
     return -1;
+  }
+  if (kind != 3 && pad == 0 && f == 1 && Hd == H && Wd == W && (Cs % 8) == 0 && (c_lo % 8) == 0 &&
+      (C % 8 == 0 || c_lo + ((C + 7) / 8) * 8 <= Cs)) {
+    // (channels up to the next multiple of 8 may be read: they exist whenever the padded extent fits in Cs)
+    dim3 grid16((H * W + 31) / 32, (C + 63) / 64, B);
+    nhwc_unpack16_kernel<<<grid16, 256, 0, stream>>>(static_cast<const uint16_t*>(src), kind == 2, Cs, c_lo, C, H * W,
+                                                     dst, Cd, cd_lo, acc);
+    COCOS_CUDA_CHECK(cudaGetLastError());
+    return 0;
   }
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
   nhwc_unpack_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, kind, Cs, c_lo, C, H, W, pad, dst, Cd, cd_lo, Hd, Wd, f,

@@ -424,3 +424,18 @@ def test_pair_loss_nhwc(mode, with_w):
     per = (d * d if mode else d.abs()).sum((1, 2, 3))
     ref = 2 * 0.37 * (per * (w if w is not None else 1.0)).sum()
     assert abs(float(got[0]) - float(ref)) < 1e-4 * abs(float(ref))
+
+
+@pytest.mark.parametrize("C,H,W,kind", [(154, 40, 24, nhwc.F16), (64, 33, 17, nhwc.BF16), (512, 16, 16, nhwc.F16)])
+def test_unpack_16bit_fast_path(C, H, W, kind):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, C, H, W, generator=g)
+    nt = nhwc.pack(x.cuda(), kind)
+    back = nhwc.unpack(nt)
+    want = x.half().float() if kind == nhwc.F16 else x.bfloat16().float()
+    assert torch.equal(back.cpu(), want)
+    out = torch.ones(2, C + 5, H, W, device="cuda")
+    nhwc.unpack(nt, c_lo=8, C=16, out=out, cd_lo=3, acc=True)
+    ref = torch.ones(2, C + 5, H, W)
+    ref[:, 3:19] += want[:, 8:24]
+    assert torch.equal(out.cpu(), ref)
