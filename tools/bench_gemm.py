@@ -18,6 +18,7 @@ for _ in range(8):
     s.record(); torch.matmul(a[0], b[0].t()); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
 ts.sort(); ms = ts[len(ts)//2]; print('cublas ms %.3f tflops %.0f' % (ms, 2*8192**3/ms/1e9))
 """
-for bn in (128, 256, 128, 256):
-    r = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, COCOS_GEMM_BN=str(bn)), capture_output=True, text=True)
-    print("BN=%d:" % bn, r.stdout.replace("\n", " | "), r.stderr[-300:] if r.returncode else "")
+for bn, two in ((128, 0), (256, 0), (256, 1), (256, 0), (256, 1)):
+    r = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, COCOS_GEMM_BN=str(bn), COCOS_GEMM_2CTA=str(two)),
+                       capture_output=True, text=True, timeout=300)
+    print("BN=%d 2cta=%d:" % (bn, two), r.stdout.replace("\n", " | "), r.stderr[-600:] if r.returncode else "")
