@@ -291,7 +291,9 @@ def main():
                               "ms_per_step": ms / args.steps, "e2e": PER_GPU_BATCH * world * args.steps / (ms_e2e / 1e3),
                               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            torch.cuda.synchronize()
+            os._exit(0)
         return 0
     roof = roof_k2304 = cpu = gpu_base = None
     if rank == 0:
@@ -350,7 +352,15 @@ def main():
                 "gpu_baseline": gpu_base, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down with a captured NCCL all-reduce alive can block in ncclCommDestroy (seen once: the N = 2 run sat
+        # until its timeout after printing its line): drop the graph, drain the device, and leave without the collective
+        # shutdown -- every rank has finished its work and rank 0 has printed
+        sys.stdout.flush()
+        trainer.free_graph()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
     return 0
 
 

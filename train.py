@@ -62,6 +62,9 @@ def main():
             trainer.save(epoch)
     print("Training was successfully finished.")
     if world > 1:
+        trainer.free_graph()  # a captured NCCL all-reduce must be gone before the communicator is destroyed
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
