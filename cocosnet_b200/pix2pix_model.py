@@ -21,6 +21,7 @@ class Pix2PixModel(torch.nn.Module):
         super().__init__()
         self.opt = opt
         self.alpha = 1
+        self.after_netG_backward = None  # trainer hook: called once the backward has left netG (its gradients are final)
         self.net = torch.nn.ModuleDict(self.initialize_networks(opt))
         if opt.isTrain:
             self.vggnet_fix = networks.VGG19_feature_color_torchversion(vgg_normal_correct=opt.vgg_normal_correct)
@@ -267,6 +268,15 @@ class Pix2PixModel(torch.nn.Module):
         ctx_keys = keys[-4:] if self.opt.use_22ctx else keys[-3:]
         gen = {"ref_features": self.vggnet_fix(ref_image, ctx_keys, preprocess=True)}
         coor_out = self.net["netCorr"](ref_image, real_image, input_semantics, ref_semantics, alpha=self.alpha)
+        if self.after_netG_backward is not None and coor_out["warp_out"].requires_grad:
+            # the gradient of netCorr's output is complete only after netG's whole backward (netG reads warp_out);
+            # autograd runs the parameters' AccumulateGrad nodes before it continues upstream
+            fire = self.after_netG_backward
+
+            def _hook(g):
+                fire()
+                return g
+            coor_out["warp_out"].register_hook(_hook)
         from .nets import fast as _fast
         if _fast.fused_losses() and _fast.vgg_supported(self.vggnet_fix, real_image):
             # the real image's VGG features stay fp16 NHWC: targets of the fused feature / perceptual losses

@@ -46,22 +46,24 @@ def shard_batch(data, rank=None, world=None):
     return out
 
 
-def allreduce_grads(params, world=None):
-    """Sum-then-average gradients across ranks, bucketed and flattened."""
+def allreduce_grads(params, world=None, async_op=False):
+    """Average the gradients across ranks.  NCCL: one grouped launch over the gradient tensors themselves; async_op
+    returns the handle to wait() on (the collective then runs on NCCL's stream beside whatever is enqueued next).
+    Other backends (gloo, the CPU tests): bucketed, flattened, summed and divided."""
     world = _world() if world is None else world
     if world == 1:
-        return 0
+        return None
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
-        return 0
+        return None
     if dist.get_backend() == "nccl":
         # ONE grouped NCCL launch over the gradient tensors themselves (ncclGroupStart / End around per-tensor
         # all-reduces, averaged in the collective): no flatten, no copy-back, no separate division -- and a fixed
         # sequence of device work, so it is captured into the iteration's CUDA graph like any other kernel.
-        with dist._coalescing_manager(device=grads[0].device, async_ops=False):
+        with dist._coalescing_manager(device=grads[0].device, async_ops=async_op) as cm:
             for g in grads:
                 dist.all_reduce(g, op=dist.ReduceOp.AVG)
-        return 1
+        return cm if async_op else None
     buckets, cur, size = [], [], 0
     for g in grads:
         cur.append(g)
@@ -83,7 +85,7 @@ def allreduce_grads(params, world=None):
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
-    return len(buckets)
+    return None
 
 
 class Pix2PixTrainer:
@@ -252,14 +254,36 @@ class Pix2PixTrainer:
         # computes and then discards them: optimizer_D.zero_grad() runs before they are ever used).
         for p in self._d_params:
             p.requires_grad_(False)
+        # more than one rank (NCCL): the generator's gradients are complete as soon as the backward leaves netG -- the
+        # hook the model places on netCorr's output fires there -- so their all-reduce (62 % of the bytes) runs on
+        # NCCL's stream underneath netCorr's backward; the rest follows after the backward
+        overlap = _world() > 1 and dist.get_backend() == "nccl" and "warp" in self.opt.CBN_intype \
+            and os.environ.get("COCOS_OVERLAP_ALLREDUCE", "1") == "1"
+        pending = []
+        if overlap:
+            netg = [p for p in self.pix2pix_model.net["netG"].parameters() if p.requires_grad]
+
+            def early():
+                # every netG parameter receives exactly one gradient per step and .grad was None before: all present
+                # == all final (otherwise nothing is started here and the whole set is reduced after the backward)
+                if all(p.grad is not None for p in netg):
+                    pending.append(allreduce_grads(netg, async_op=True))
+            self.pix2pix_model.after_netG_backward = early
         try:
             g_losses, out = self.pix2pix_model(self._shard(data), mode="generator", alpha=alpha)
             g_loss = sum(g_losses.values()).mean()
             g_loss.backward()
         finally:
+            self.pix2pix_model.after_netG_backward = None
             for p in self._d_params:
                 p.requires_grad_(True)
-        allreduce_grads(self._g_params)
+        if overlap and pending:
+            allreduce_grads([p for p in self.pix2pix_model.net["netCorr"].parameters()])
+            for h in pending:
+                if h is not None:
+                    h.wait()
+        else:
+            allreduce_grads(self._g_params)
         self.optimizer_G.step()
         self.g_losses, self.out = g_losses, out
         if self.opt.use_ema:
