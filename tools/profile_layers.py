@@ -25,6 +25,9 @@ def _nt_bytes(nt, C=None):
 
 def _sig_conv(x, w, bias, res, y, d):
     work = 2.0 * d["B"] * d["H"] * d["W"] * d["Cout"] * len(d["groups"]) * d["kchunks"] * 64
+    if d.get("mod") is not None:
+        return ("tapconv_spade %dx%d Ca%d->2x%d g%d kc%d B%d" % (d["H"], d["W"], d["Ca"], d["Cout"] // 2, len(d["groups"]),
+                                                                 d["kchunks"], d["B"]), work, "flop")
     return ("tapconv%s s%d %dx%d Ca%d->%d g%d kc%d B%d%s" % ("_bf16" if d["bf16"] else "", d["a_stride"], d["H"], d["W"],
                                                           d["Ca"], d["Cout"], len(d["groups"]), d["kchunks"], d["B"],
                                                           " ->nchw" if d["y_kind"] == 0 else ""), work, "flop")
@@ -44,7 +47,7 @@ def _sig_spade_fwd(x, gb, y, mean, rstd, C, pad, slope, eps):
     return ("spade_fwd %dx%d C%d xk%d" % (x.H, x.W, C, x.kind), _nt_bytes(x, C) + _nt_bytes(gb, 2 * C) + y.t.numel() * 2.0, "byte")
 
 
-def _sig_spade_bwd(dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope):
+def _sig_spade_bwd(dy, x, gb, mean, rstd, dx, dx_acc, dgb, C, pad, slope, gb_W=0):
     return ("spade_bwd %dx%d C%d xk%d" % (x.H, x.W, C, x.kind),
             dy.t.numel() * 2.0 + _nt_bytes(x, C) + _nt_bytes(gb, 2 * C) + (2 if dx_acc else 1) * dx.t.numel() * 2.0 + dgb.t.numel() * 2.0,
             "byte")
@@ -54,13 +57,14 @@ def _sig_in_stats(x, stats, C):
     return ("in_stats %dx%d C%d xk%d" % (x.H, x.W, C, x.kind), _nt_bytes(x), "byte")
 
 
-def _sig_inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, C):
+def _sig_inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, C, gb=None, batch_stats=False):
     b = _nt_bytes(x) + y.t.numel() * _BYTES[y.kind] + (res.t.numel() * _BYTES[res.kind] if res else 0) + \
         (y2.t.numel() * 4 if y2 else 0)
     return ("inst_fwd %dx%d C%d xk%d%s" % (x.H, x.W, C, x.kind, " +res" if res else ""), b, "byte")
 
 
-def _sig_inst_bwd(dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C):
+def _sig_inst_bwd(dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres, dres_acc, eps, C, gb=None,
+                  dgb=None, batch_stats=False, const_stats=False, phase=0):
     b = 2 * (dy.t.numel() * 2.0 + _nt_bytes(x) + (res.t.numel() * _BYTES[res.kind] if res else 0)
              + (dy2.t.numel() * 2.0 if dy2 else 0)) + dx.t.numel() * 2.0 + (dres.t.numel() * 2.0 if dres else 0)
     return ("inst_bwd %dx%d C%d xk%d%s" % (x.H, x.W, C, x.kind, " +res" if res else ""), b, "byte")
@@ -92,7 +96,24 @@ def _sig_maxpool_bwd(dy, x, dx):
     return ("maxpool_bwd %dx%d Cs%d" % (x.H, x.W, x.Cs), x.t.numel() * 2.0 * 2.25, "byte")
 
 
-SIGS = {"tapconv": _sig_conv, "tapwgrad": _sig_wgrad, "pack_w": _sig_packw, "spade_fwd": _sig_spade_fwd,
+def _sig_pair_fwd(x, y, w, scale, mode, out):
+    return ("pair_loss_fwd %dx%d C%d" % (x.H, x.W, x.C), 2.0 * x.t.numel() * 2, "byte")
+
+
+def _sig_pair_bwd(x, y, w, scale, mode, g, dx, acc):
+    return ("pair_loss_bwd %dx%d C%d" % (x.H, x.W, x.C), (3.0 + (1 if acc else 0)) * x.t.numel() * 2, "byte")
+
+
+def _sig_cast(x, dst):
+    return ("cast_bf16 %dx%d Cs%d" % (x.H, x.W, x.Cs), x.t.numel() * 2.0 + dst.t.numel() * 2.0, "byte")
+
+
+def _sig_pono(x, C, eps, mean, rstd):
+    return ("pono_stats %dx%d C%d xk%d" % (x.H, x.W, C, x.kind), _nt_bytes(x, C), "byte")
+
+
+SIGS = {"pair_loss_fwd": _sig_pair_fwd, "pair_loss_bwd": _sig_pair_bwd, "cast_bf16": _sig_cast, "pono_stats": _sig_pono,
+        "tapconv": _sig_conv, "tapwgrad": _sig_wgrad, "pack_w": _sig_packw, "spade_fwd": _sig_spade_fwd,
         "spade_bwd": _sig_spade_bwd, "in_stats": _sig_in_stats, "inst_fwd": _sig_inst_fwd, "inst_bwd": _sig_inst_bwd,
         "act_bwd": _sig_act_bwd, "pack": _sig_pack, "unpack": _sig_unpack, "colsum": _sig_colsum,
         "maxpool_fwd": _sig_maxpool_fwd, "maxpool_bwd": _sig_maxpool_bwd}
