@@ -34,11 +34,14 @@ class ParamSet:
     def __init__(self):
         self._tensors, self.slot, self.params = [], {}, None
         self._sn, self._sn_vec = [], {}
+        self._persistent = set()
 
     def _add(self, key, t):
         if key not in self.slot:
             self.slot[key] = len(self._tensors)
             self._tensors.append(t)
+            if isinstance(t, nn.Parameter):  # a module's own parameter (not a tensor computed from parameters)
+                self._persistent.add(self.slot[key])
 
     @property
     def tensors(self):
@@ -90,6 +93,8 @@ class ParamSet:
 
     def bind(self, params):
         self.params = params
+        for i in self._persistent:
+            params[i].cache = self._tensors[i]
         for (kind, key), i in self.slot.items():
             if kind == "s":
                 w = params[self.slot[("w", key)]]

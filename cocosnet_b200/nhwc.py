@@ -11,6 +11,8 @@ Reference call sites served: every nn.Conv2d of models/networks/{generator,archi
 discriminator}.py plus the norm / activation / padding modules between them.
 """
 import ctypes
+import os as _os
+import weakref as _weakref
 
 import torch
 
@@ -406,16 +408,45 @@ def unpack(x, c_lo=0, C=None, out=None, cd_lo=0, f=1, acc=False):
 
 
 # ------------------------------------------------------------------------------------------------ convolution
-def _pack_weight(weight, groups, rows, kc, transposed, bf16):
+# Packed weight matrices are reused while the parameter is unchanged: the key holds the tensor's address AND its
+# version counter (every in-place optimiser update bumps it), so a layer that runs several times between two updates --
+# the image adaptor (exemplar + real image), the discriminators (generator step: fake and real halves, then the
+# discriminator step), the frozen VGG19 (three passes + one backward) -- is packed once.  One entry per (tensor, layout).
+# A CUDA-graph replay updates parameters WITHOUT touching version counters: the trainer clears the cache around
+# captures and replays (clear_pack_cache), so nothing packed inside a graph is ever trusted outside it.
+_PACK_CACHE = {}
+PACK_CACHE = _os.environ.get("COCOS_PACK_CACHE", "1") != "0"
+
+
+def clear_pack_cache():
+    _PACK_CACHE.clear()
+
+
+def _pack_weight(weight, groups, rows, kc, transposed, bf16, cache=None):
+    """cache: the nn.Parameter object `weight` is the data of (a persistent tensor: stable address, version bumped by
+    every in-place update), or None.  Computed weights (concatenations, permutations) are new tensors every forward
+    whose addresses the allocator recycles: never cached.  An entry is only trusted while that very Parameter object is
+    alive (a later model's parameter may land on the same address with the same version)."""
     be = backend()
     rows_alloc = round_up(rows, 128)
+    w = weight.detach()
+    key = ver = None
+    if cache is not None and PACK_CACHE and w.is_contiguous() and w.data_ptr() == cache.data_ptr():
+        key = (id(cache), w.data_ptr(), tuple(w.shape), rows, kc, bool(transposed), bool(bf16),
+               tuple((g.r, g.s, g.term) for g in groups))
+        ver = cache._version
+        hit = _PACK_CACHE.get(key)
+        if hit is not None and hit[0] == ver and hit[2]() is cache:
+            return hit[1], rows_alloc
     dst = be.empty((rows_alloc, len(groups) * kc), BF16 if bf16 else F16, weight.device)
-    be.pack_w(weight.detach().contiguous(), dst, rows, rows_alloc, kc, groups, transposed, bf16)
+    be.pack_w(w.contiguous(), dst, rows, rows_alloc, kc, groups, transposed, bf16)
+    if key is not None:
+        _PACK_CACHE[key] = (ver, dst, _weakref.ref(cache))
     return dst, rows_alloc
 
 
 def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kind=F16, out_pad=0, split_out=False,
-         res=None, nchw_out=None, nchw_coff=0, wsplit=None, scale=None):
+         res=None, nchw_out=None, nchw_coff=0, wsplit=None, scale=None, cache_w=None):
     """nn.Conv2d forward on the tap-convolution kernel.  x: NT fp16 (its tensor, halo included, IS the conv input;
     `padding` is the module's zero padding).  scale: 1-element fp32 device tensor multiplied into the accumulator
     before the bias (spectral norm's 1/sigma: `weight` stays the un-normalised weight_orig).  Returns an NT of kind out_kind (op tensors: out_pad = 1 adds the
@@ -428,7 +459,7 @@ def conv(x, weight, bias=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out
     h, w = conv_out_size(hin, ks, padding, stride), conv_out_size(win, ks, padding, stride)
     groups = plan_fwd(ks, padding, x.lo, wsplit)
     kchunks = (cin + 63) // 64
-    wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False)
+    wp, rows_alloc = _pack_weight(weight, groups, cout, kchunks * 64, False, False, cache=cache_w)
     d = dict(B=x.B, Hin=hin, Win=win, Ca=x.Cs, a_stride=stride, bf16=0, H=h, W=w, Cout=cout, w_rows=rows_alloc,
              kchunks=kchunks, groups=groups, res_kind=res.kind if res else 0, res_Cs=res.Cs if res else 0, act=act,
              slope=slope, scale=scale, y_H=h, y_W=w, y_coff=0, y_lo_off=0, y_pad=0, y_reflect=0, y_sh=1, y_sw=1, y_oh=0, y_ow=0)
@@ -491,7 +522,7 @@ def conv_spade(actv, weight, bias, x, C, pad, slope, eps=1e-5, split_out=False, 
     return y, gb, mean, rstd
 
 
-def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=None, scale=None):
+def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=None, scale=None, cache_w=None):
     """Backward-data: dy NT bf16 [B,H,W,Cout] -> gradient w.r.t. the conv input tensor (halo included) as an NT bf16
     with pad = in_pad (the consumer folds the halo).  in_hw = (Hin, Win) of the input tensor incl. halo.
     c_lo / c_n: only input channels [c_lo, c_lo + c_n) are produced."""
@@ -505,7 +536,7 @@ def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=Non
     kchunks = (cout + 63) // 64
     out = new(dy.B, hin - 2 * in_pad, win - 2 * in_pad, c_n, BF16, dy.t.device, pad=in_pad)
     for pi, pj, groups in plan_dgrad(ks, padding, stride):
-        wp, rows_alloc = _pack_weight(wsub, groups, c_n, kchunks * 64, True, True)
+        wp, rows_alloc = _pack_weight(wsub, groups, c_n, kchunks * 64, True, True, cache=cache_w if wsub is weight else None)
         hc, wc = (hin - pi + stride - 1) // stride, (win - pj + stride - 1) // stride
         d = dict(B=dy.B, Hin=dy.t.shape[1], Win=dy.t.shape[2], Ca=dy.Cs, a_stride=1, bf16=1, H=hc, W=wc, Cout=c_n,
                  w_rows=rows_alloc, kchunks=kchunks, groups=groups, res_kind=0, res_Cs=0, act=ACT_NONE, slope=0.0,
@@ -514,8 +545,6 @@ def conv_dgrad(dy, weight, in_hw, stride=1, padding=0, in_pad=0, c_lo=0, c_n=Non
         backend().tapconv(dy.t, wp, None, None, out.t, d)
     return out
 
-
-import os as _os
 
 # X of the backward-weights GEMM converted to bf16 by a separate HBM-bound pass (0: inside the GEMM kernel, A/B runs)
 WGRAD_BF16_X = _os.environ.get("COCOS_WGRAD_BF16_X", "1") != "0"

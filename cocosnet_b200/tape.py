@@ -25,10 +25,11 @@ class Var:
 class Param:
     """A weight / bias of the boundary Function (fp32 torch tensor); g accumulates its gradient.  scale: the Param of
     the 1-element factor the convolution applies in its epilogue (spectral norm: t = weight_orig, scale = 1/sigma)."""
-    __slots__ = ("t", "g", "need", "scale", "sn")
+    __slots__ = ("t", "g", "need", "scale", "sn", "cache")
 
     def __init__(self, t, need=True):
         self.t, self.g, self.need, self.scale = t, None, need, None
+        self.cache = None  # the nn.Parameter t is the data of: its packed forms may be reused while its version stands
         self.sn = None  # (u, v) of the spectral norm whose 1/sigma is `scale`: d sigma / d weight = u v^T
 
     def add(self, g):
@@ -176,7 +177,7 @@ def _conv_backward(x, W, b, dz, stride, padding, dx_ch):
     if x.need:
         c_lo, c_n = dx_ch if dx_ch is not None else (0, None)
         dx = nhwc.conv_dgrad(dz, W.t, (xv.t.shape[1], xv.t.shape[2]), stride=stride, padding=padding,
-                             in_pad=xv.pad, c_lo=c_lo, c_n=c_n, scale=sc)
+                             in_pad=xv.pad, c_lo=c_lo, c_n=c_n, scale=sc, cache_w=W.cache)
         acc(x, dx)
 
 
@@ -193,12 +194,12 @@ def conv(tp, x, W, b=None, stride=1, padding=0, act=ACT_NONE, slope=0.0, out_kin
         w = nhwc.conv_out_size(xv.t.shape[2], ks, padding, stride)
         y = torch.empty((xv.B, W.t.shape[0], h, w), dtype=torch.float32, device=xv.t.device)
         nhwc.conv(xv, W.t, None if b is None else b.t, stride=stride, padding=padding, act=act, slope=slope,
-                  nchw_out=y, wsplit=wsplit, scale=sc)
+                  nchw_out=y, wsplit=wsplit, scale=sc, cache_w=W.cache)
         out = None
     else:
         y = nhwc.conv(xv, W.t, None if b is None else b.t, stride=stride, padding=padding, act=act, slope=slope,
                       out_kind=out_kind, out_pad=out_pad, split_out=split_out, res=None if res is None else res.v,
-                      wsplit=wsplit, scale=sc)
+                      wsplit=wsplit, scale=sc, cache_w=W.cache)
         out = Var(y)
 
     def backward_from(dz):

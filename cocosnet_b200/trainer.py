@@ -16,7 +16,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import util
+from . import nhwc, util
 from .nets import EMA
 from .pix2pix_model import Pix2PixModel
 
@@ -181,6 +181,7 @@ class Pix2PixTrainer:
             return self._eager_step(data, alpha)  # e.g. the short last batch of an epoch: not the captured shapes
         self._load_static(data)
         self._graph.replay()
+        nhwc.clear_pack_cache()  # the replay changed parameters without bumping their version counters
 
     def free_graph(self):
         """Drop the captured iteration and its private memory pool (it is re-captured on the next run_step)."""
@@ -214,6 +215,7 @@ class Pix2PixTrainer:
         gc.collect()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        nhwc.clear_pack_cache()  # everything the graph reads must be produced inside it (or be immutable)
         l0 = _lib.LAUNCHES
         err = None
         try:
@@ -241,6 +243,7 @@ class Pix2PixTrainer:
             return
         self.graph_native_launches = _lib.LAUNCHES - l0
         self._graph = graph
+        nhwc.clear_pack_cache()  # buffers packed during the capture live in the graph's pool: not for eager use
         self._graph_key_captured = self._graph_key(alpha)
 
     def _shard(self, data):

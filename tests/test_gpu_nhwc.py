@@ -439,3 +439,29 @@ def test_unpack_16bit_fast_path(C, H, W, kind):
     ref = torch.ones(2, C + 5, H, W)
     ref[:, 3:19] += want[:, 8:24]
     assert torch.equal(out.cpu(), ref)
+
+
+def test_packed_weight_cache_follows_the_parameter_version():
+    """The packed-weight cache: reused while the nn.Parameter is unchanged, refreshed by an in-place update, never
+    shared with another Parameter object (even one that lands on the freed address)."""
+    g = torch.Generator().manual_seed(3)
+    x = nhwc.pack(torch.randn(1, 64, 16, 16, generator=g).cuda(), nhwc.F16)
+    p = torch.nn.Parameter((torch.randn(64, 64, 3, 3, generator=g) * 0.05).cuda())
+    from cocosnet_b200 import _lib
+    nhwc.clear_pack_cache()
+    n0 = _lib.LAUNCHES
+    y1 = nhwc.conv(x, p, None, padding=1, out_kind=nhwc.F32, cache_w=p).t.clone()
+    n1 = _lib.LAUNCHES
+    y1b = nhwc.conv(x, p, None, padding=1, out_kind=nhwc.F32, cache_w=p).t.clone()
+    n2 = _lib.LAUNCHES
+    assert n1 - n0 == 2 and n2 - n1 == 1          # pack + conv, then conv only
+    assert torch.equal(y1, y1b)
+    with torch.no_grad():
+        p.mul_(2.0)                                # what an optimiser step does: in place, version bumped
+    y2 = nhwc.conv(x, p, None, padding=1, out_kind=nhwc.F32, cache_w=p).t
+    assert rel(y2, 2 * y1) < 1e-6
+    addr = p.data_ptr()
+    del p
+    q = torch.nn.Parameter(torch.zeros(64, 64, 3, 3, device="cuda"))   # very likely the recycled address
+    y3 = nhwc.conv(x, q, None, padding=1, out_kind=nhwc.F32, cache_w=q).t
+    assert float(y3.abs().max()) == 0.0, "stale packed weights (address reuse %s)" % (q.data_ptr() == addr)
