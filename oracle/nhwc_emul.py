@@ -335,7 +335,9 @@ class EmulBackend:
 
     def cast_bf16(self, x, dst):
         cs = dst.t.shape[3]
-        v = x.t.float()[..., :cs] + (x.t.float()[..., x.lo:x.lo + cs] if x.lo else 0)
+        v = x.t.float()[..., :cs]
+        if self.exact and x.lo:  # exact mode keeps every tensor in fp32: hi alone would drop real bits
+            v = v + x.t.float()[..., x.lo:x.lo + cs]
         dst.t.copy_(v.to(dst.t.dtype))
 
     def maxpool_fwd(self, x, y):
