@@ -384,12 +384,20 @@ struct InstBwd {
   int const_stats;                       // eval-mode BatchNorm: the statistics do not depend on x (no mean terms)
 };
 
-// dz for 4 channels of one source pixel (shared by both passes)
+// dz for 4 channels of one source pixel (shared by both passes).  MODE < 0: every option read from the descriptor at run
+// time; MODE = xf32 | res << 1 | pad << 2 | dy2 << 3 (no modulation, residual of x's kind): the options are compile-time
+// constants, so the loop bodies are straight-line code whose loads the compiler can hoist and batch.
+template <int MODE>
 __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, int b, int pix, int c, float slope,
                                             float* z, float* dz, float* u_neg_dy, float* dact) {
+  constexpr bool GEN = MODE < 0;
+  const int xk = GEN ? p.x_kind : ((MODE & 1) ? 3 : 1);
+  const bool has_res = GEN ? (p.res != nullptr) : ((MODE & 2) != 0);
+  const bool has_pad = GEN ? (p.dy_pad != 0) : ((MODE & 4) != 0);
+  const bool has_dy2 = GEN ? (p.dy2 != nullptr) : ((MODE & 8) != 0);
   const size_t spix = static_cast<size_t>(b) * p.H * p.W + pix;
   float4 d;
-  if (p.dy_pad) {
+  if (has_pad) {
     const int Wp = p.W + 2 * p.dy_pad, Hp = p.H + 2 * p.dy_pad;
     const int h = pix / p.W, w = pix - h * p.W;
     const Fold f = make_fold(h, w, p.H, p.W, p.dy_pad);
@@ -397,18 +405,18 @@ __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, in
   } else {
     d = ld4(p.dy, 2, spix * p.dy_Cs + c);
   }
-  if (p.dy2) {
+  if (has_dy2) {
     const float4 t = ld4(p.dy2, 2, spix * p.dy2_Cs + c);
     d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
   }
-  const float4 v = ld4(p.x, p.x_kind, spix * p.x_Cs + c);
+  const float4 v = ld4(p.x, xk, spix * p.x_Cs + c);
   float rs[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p.res) {
-    const float4 t = ld4(p.res, p.res_kind, spix * p.res_Cs + c);
+  if (has_res) {
+    const float4 t = ld4(p.res, GEN ? p.res_kind : xk, spix * p.res_Cs + c);
     rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w;
   }
   float g1[4] = {1.f, 1.f, 1.f, 1.f};
-  if (p.gb) {
+  if (GEN && p.gb) {
     const float4 g = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + c), be = ld4(p.gb, p.gb_kind, spix * p.gb_Cs + p.C + c);
     g1[0] += g.x; g1[1] += g.y; g1[2] += g.z; g1[3] += g.w;
     rs[0] += be.x; rs[1] += be.y; rs[2] += be.z; rs[3] += be.w;
@@ -425,6 +433,7 @@ __device__ __forceinline__ void inst_bwd_dz(const InstBwd& p, const Coef4& k, in
 }
 
 // pass 1: bstats += {sum dz, sum dz*z}, dslope += sum dy*u*[u<=0]
+template <int MODE>
 __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const InstBwd p, int pix_per_block) {
   __shared__ float red[8][32][8];
   __shared__ float red_s[8][32];
@@ -439,10 +448,10 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
   if (c < p.C) {
     const float cnt = p.batch_stats ? static_cast<float>(p.B) * HW : static_cast<float>(HW);
     const Coef4 k = load_coef4(p.stats, b, p.C, c, 1.0f / cnt, p.eps, p.batch_stats ? 0 : 1);
-#pragma unroll 2
+#pragma unroll 4
     for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
       float z[4], dz[4], un[4], da[4];
-      inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un, da);
+      inst_bwd_dz<MODE>(p, k, b, pix, c, slope, z, dz, un, da);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s[j] += dz[j];
@@ -485,6 +494,7 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_stats_kernel(const Inst
 }
 
 // pass 2: dx = rstd * (dz - mean(dz) - z * mean(dz*z)); dres = dz
+template <int MODE>
 __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const InstBwd p, int pix_per_block) {
   const int b = blockIdx.z;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
@@ -503,10 +513,10 @@ __global__ void __launch_bounds__(256) inst_act_nhwc_bwd_apply_kernel(const Inst
     m1[j] = p.const_stats ? 0.f : bs.x * inv;
     m2[j] = p.const_stats ? 0.f : bs.y * inv;
   }
-#pragma unroll 2
+#pragma unroll 4
   for (int pix = p0 + threadIdx.y; pix < p1; pix += 8) {
     float z[4], dz[4], un[4], o[4], da[4];
-    inst_bwd_dz(p, k, b, pix, c, slope, z, dz, un, da);
+    inst_bwd_dz<MODE>(p, k, b, pix, c, slope, z, dz, un, da);
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = k.rstd[j] * (dz[j] - m1[j] - z[j] * m2[j]);
     const size_t spix = static_cast<size_t>(b) * HW + pix;
@@ -1053,15 +1063,27 @@ int inst_act_nhwc_bwd_launch(const void* dy, int dy_Cs, int dy_pad, const void* 
   int ppb;
   stats_grid(H * W, C, B, &grid, &block, &ppb);
   // phase 1: statistics only, phase 2: apply only (a synchronised BatchNorm all-reduces bstats in between), 0: both
-  if (phase != 2) {
+  // specialised variants: no modulation, 16-bit or fp32 x, residual (if any) of x's kind
+  int mode = -1;
+  if (!gb && (x_kind == 1 || x_kind == 3) && (!res || res_kind == x_kind))
+    mode = (x_kind == 3 ? 1 : 0) | (res ? 2 : 0) | (dy_pad ? 4 : 0) | (dy2 ? 8 : 0);
+#define COCOS_INST_BWD(M)                                                                      \
+  case M:                                                                                      \
+    if (phase != 2) inst_act_nhwc_bwd_stats_kernel<M><<<grid, block, 0, stream>>>(p, ppb);     \
+    if (phase != 1) inst_act_nhwc_bwd_apply_kernel<M><<<grid, block, 0, stream>>>(p, ppb);     \
+    break;
+  if (phase != 2)
     COCOS_CUDA_CHECK(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * (batch_stats ? 1 : B) * C, stream));
-    inst_act_nhwc_bwd_stats_kernel<<<grid, block, 0, stream>>>(p, ppb);
-    COCOS_CUDA_CHECK(cudaGetLastError());
+  switch (mode) {
+    COCOS_INST_BWD(0) COCOS_INST_BWD(1) COCOS_INST_BWD(2) COCOS_INST_BWD(3) COCOS_INST_BWD(4) COCOS_INST_BWD(5)
+    COCOS_INST_BWD(6) COCOS_INST_BWD(7) COCOS_INST_BWD(8) COCOS_INST_BWD(9) COCOS_INST_BWD(10) COCOS_INST_BWD(11)
+    COCOS_INST_BWD(12) COCOS_INST_BWD(13) COCOS_INST_BWD(14) COCOS_INST_BWD(15)
+    default:
+      if (phase != 2) inst_act_nhwc_bwd_stats_kernel<-1><<<grid, block, 0, stream>>>(p, ppb);
+      if (phase != 1) inst_act_nhwc_bwd_apply_kernel<-1><<<grid, block, 0, stream>>>(p, ppb);
   }
-  if (phase != 1) {
-    inst_act_nhwc_bwd_apply_kernel<<<grid, block, 0, stream>>>(p, ppb);
-    COCOS_CUDA_CHECK(cudaGetLastError());
-  }
+#undef COCOS_INST_BWD
+  COCOS_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
