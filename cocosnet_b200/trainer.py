@@ -141,8 +141,13 @@ class Pix2PixTrainer:
                 and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
-        self.run_generator_one_step(data, alpha)
+        # with more than one rank the generator's gradient all-reduces keep running on NCCL's stream underneath the
+        # whole discriminator step (which reads neither netG nor netCorr parameters): optimizer_G.step() is deferred
+        # until after it -- the same updates in the same order per network, nothing exposed but the small D all-reduce
+        finish = self.run_generator_one_step(data, alpha, defer_step=True)
         self.run_discriminator_one_step(data)
+        if finish is not None:
+            finish()
 
     def _load_static(self, data):
         for k, buf in self._static_in.items():
@@ -251,7 +256,9 @@ class Pix2PixTrainer:
         (a per-rank data loader, bench.py's weak-scaling batches)."""
         return data if self.pre_sharded else shard_batch(data)
 
-    def run_generator_one_step(self, data, alpha=1):
+    def run_generator_one_step(self, data, alpha=1, defer_step=False):
+        """defer_step (only honoured with NCCL ranks): return a callable that waits for the gradient all-reduces and
+        applies optimizer_G.step() (+ EMA) instead of doing so here."""
         self.optimizer_G.zero_grad(set_to_none=True)
         # The G step only needs the gradient THROUGH the discriminator, not its weight gradients (the reference
         # computes and then discards them: optimizer_D.zero_grad() runs before they are ever used).
@@ -280,18 +287,25 @@ class Pix2PixTrainer:
             self.pix2pix_model.after_netG_backward = None
             for p in self._d_params:
                 p.requires_grad_(True)
+        self.g_losses, self.out = g_losses, out
         if overlap and pending:
-            allreduce_grads([p for p in self.pix2pix_model.net["netCorr"].parameters()])
+            pending.append(allreduce_grads([p for p in self.pix2pix_model.net["netCorr"].parameters()], async_op=defer_step))
+        else:
+            allreduce_grads(self._g_params)
+            pending = []
+
+        def finish():
             for h in pending:
                 if h is not None:
                     h.wait()
-        else:
-            allreduce_grads(self._g_params)
-        self.optimizer_G.step()
-        self.g_losses, self.out = g_losses, out
-        if self.opt.use_ema:
-            self.netG_ema(self.pix2pix_model.net["netG"])
-            self.netCorr_ema(self.pix2pix_model.net["netCorr"])
+            self.optimizer_G.step()
+            if self.opt.use_ema:
+                self.netG_ema(self.pix2pix_model.net["netG"])
+                self.netCorr_ema(self.pix2pix_model.net["netCorr"])
+        if defer_step and overlap and pending:
+            return finish
+        finish()
+        return None
 
     def run_discriminator_one_step(self, data):
         self.optimizer_D.zero_grad(set_to_none=True)
