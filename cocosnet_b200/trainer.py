@@ -141,10 +141,12 @@ class Pix2PixTrainer:
                 and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
-        # with more than one rank the generator's gradient all-reduces keep running on NCCL's stream underneath the
-        # whole discriminator step (which reads neither netG nor netCorr parameters): optimizer_G.step() is deferred
-        # until after it -- the same updates in the same order per network, nothing exposed but the small D all-reduce
-        finish = self.run_generator_one_step(data, alpha, defer_step=True)
+        # EXPERIMENTAL (COCOS_DEFER_G_STEP=1, off by default): keep the generator's gradient all-reduces running on
+        # NCCL's stream underneath the whole discriminator step (which reads neither netG nor netCorr parameters) and
+        # defer optimizer_G.step() until after it.  Measured 0.987 at N = 2, but the N = 8 run did not finish within its
+        # time limit (profiles/r02_scale_README.txt), so the validated schedule stays the default: netG's all-reduce
+        # under netCorr's backward, the rest and the optimiser step right after the backward.
+        finish = self.run_generator_one_step(data, alpha, defer_step=os.environ.get("COCOS_DEFER_G_STEP", "0") == "1")
         self.run_discriminator_one_step(data)
         if finish is not None:
             finish()
