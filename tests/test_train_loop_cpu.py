@@ -59,3 +59,50 @@ def test_ema_updates_in_place():
     assert lin.weight.data_ptr() == wptr and torch.allclose(lin.weight.data, ema.shadow["weight"])
     ema.resume(lin)
     assert lin.weight.data_ptr() == wptr and torch.allclose(lin.weight.data, w0 + 1)
+
+
+def test_netG_gradients_are_final_when_the_overlap_hook_fires(monkeypatch, tmp_path):
+    """The multi-rank schedule starts netG's gradient all-reduce from an autograd hook on netCorr's output.  That is only
+    sound if, when the hook fires, every netG parameter already holds its FINAL gradient of the step.  Checked here on
+    the CPU autograd engine (same engine, same node priorities as on the GPU) with the collectives replaced by
+    recorders: the early set is exactly netG's parameters, their gradients do not change afterwards, the rest is
+    reduced after the backward and the optimiser steps last."""
+    from cocosnet_b200 import trainer as tmod
+    from cocosnet_b200.trainer import Pix2PixTrainer
+    opt = TrainOptions().parse(["--dataset_mode", "ade20k", "--use_attention", "--maskmix", "--PONO", "--PONO_C",
+                                "--batchSize", "1", "--gpu_ids", "-1", "--checkpoints_dir", str(tmp_path), "--name", "t"],
+                               save=False, verbose=False)
+    opt.verbose_networks = False
+    opt.allow_random_vgg = True
+    torch.manual_seed(0)
+    trainer = Pix2PixTrainer(opt)
+    trainer.pre_sharded = True  # the batch below is this "rank"'s shard
+    batch = cdata.synthetic_batch(opt, 1)
+    events = []
+
+    class Handle:
+        def wait(self):
+            events.append(("wait",))
+
+    def fake_allreduce(params, world=None, async_op=False):
+        params = list(params)
+        events.append(("allreduce", async_op, [id(p) for p in params], [p.grad.clone() for p in params]))
+        return Handle() if async_op else None
+
+    monkeypatch.setattr(tmod, "allreduce_grads", fake_allreduce)
+    monkeypatch.setattr(tmod, "_world", lambda: 2)
+    monkeypatch.setattr(tmod.dist, "get_backend", lambda *a, **k: "nccl")
+    real_step = trainer.optimizer_G.step
+    monkeypatch.setattr(trainer.optimizer_G, "step", lambda *a, **k: (events.append(("step",)), real_step(*a, **k))[1])
+    from oracle import torch_port
+    with torch_port.cpu_reference_mode():
+        trainer.run_generator_one_step(batch)
+    kinds = [e[0] for e in events]
+    assert kinds == ["allreduce", "allreduce", "wait", "step"], kinds
+    early, late = events[0], events[1]
+    netg = list(trainer.pix2pix_model.net["netG"].parameters())
+    netc = list(trainer.pix2pix_model.net["netCorr"].parameters())
+    assert early[1] is True and early[2] == [id(p) for p in netg if p.requires_grad]
+    assert late[1] is False and late[2] == [id(p) for p in netc]
+    for p, g_then in zip([p for p in netg if p.requires_grad], early[3]):
+        assert torch.equal(p.grad, g_then), "a netG gradient changed after the hook fired"
