@@ -130,6 +130,64 @@ def k1_roofline(torch, batch=8, n=4096, kd=256, cv=3, iters=20):
             "algorithmic_flops_per_launch": flops}
 
 
+def tapconv_roofline(torch, batch=8, hw=64, cin=512, cout=512, iters=10, device="cuda"):
+    """The tap convolution alone on the generator's 512 -> 512 3x3 layer at 64x64 (generator.py:36-37), as the step
+    launches it: once with single fp16 operands (1 MMA per tap: executed == algorithmic FLOPs) and once with 2-term
+    split operands (3 MMAs per tap, the default 1e-3-parity mode upstream of warp_out / fake_image).  Weights packed
+    before the timed launches, operands resident, CUDA events around each launch, L2 flushed in between."""
+    import time
+    from cocosnet_b200 import nhwc
+    cuda = str(device).startswith("cuda")
+    g = torch.Generator(device=device).manual_seed(2)
+    x = torch.randn(batch, cin, hw, hw, device=device, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device=device, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, device=device, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if cuda else None
+    be = nhwc.backend()
+    algorithmic = 2.0 * batch * hw * hw * cout * cin * 9
+    peak, _, src = measured_peaks()
+    out = {"bound": "tensor", "kernel": "tapconv_kernel<256> (persistent TMA + tcgen05 tap convolution)",
+           "shape": {"batch": batch, "H": hw, "W": hw, "Cin": cin, "Cout": cout, "taps": 9},
+           "algorithmic_flops_per_launch": algorithmic, "peak": peak, "peak_source": src + " cuBLAS bf16 burst",
+           "unit": "TFLOP/s"}
+    for name, split in (("single", False), ("split3", True)):
+        xin = nhwc.pack(x, nhwc.F16, pad=1, split=split)
+        captured = []
+        orig = be.tapconv
+
+        def grab(*a, **k):
+            captured.append((a, k))
+            return orig(*a, **k)
+        be.tapconv = grab
+        try:
+            nhwc.conv(xin, wt, bias, padding=0, out_kind=nhwc.F16, out_pad=1)
+        finally:
+            del be.tapconv  # back to the class's method
+        (a, k), = captured
+        terms = len(a[5]["groups"]) // 9
+        for _ in range(3 if cuda else 0):
+            be.tapconv(*a, **k)
+        ts = []
+        for _ in range(iters):
+            if cuda:
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                be.tapconv(*a, **k)
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            else:
+                t0 = time.perf_counter()
+                be.tapconv(*a, **k)
+                ts.append((time.perf_counter() - t0) * 1e3)
+        ms = sum(ts) / len(ts)
+        out[name] = {"ms_per_launch": ms, "mma_terms_per_tap": terms, "achieved": algorithmic / ms / 1e9,
+                     "executed": terms * algorithmic / ms / 1e9, "frac": algorithmic / ms / 1e9 / peak,
+                     "frac_executed": terms * algorithmic / ms / 1e9 / peak}
+    return out
+
+
 def cpu_step_images_per_sec(steps, warmup, budget_s=240.0):
     """The reference's train step on host cores (CPU port, oracle/torch_port.py), batch 1 per step.
     Bounded: stops once `budget_s` is spent; with a single completed step that (cold) step is the sample."""
@@ -295,10 +353,14 @@ def main():
             torch.cuda.synchronize()
             os._exit(0)
         return 0
-    roof = roof_k2304 = cpu = gpu_base = None
+    roof = roof_k2304 = roof_conv = cpu = gpu_base = None
     if rank == 0:
         roof = k1_roofline(torch)
         roof_k2304 = k1_roofline(torch, kd=2304, iters=10)  # the K the train step itself runs (match_kernel 3)
+        try:
+            roof_conv = tapconv_roofline(torch)  # the kernel family with the largest share of the step
+        except Exception as e:  # noqa: BLE001 -- an explanatory extra: never at the price of the line itself
+            roof_conv = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
@@ -348,7 +410,8 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": gb * args.steps / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roof, "roofline_k2304": roof_k2304, "step_roofline": step_roof,
+                "gpu_launches": launches, "roofline": roof, "roofline_k2304": roof_k2304, "roofline_tapconv": roof_conv,
+                "step_roofline": step_roof,
                 "gpu_baseline": gpu_base, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

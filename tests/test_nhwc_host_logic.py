@@ -178,3 +178,21 @@ def test_plan_dgrad_covers_every_tap_once():
     for ks, padding, stride in itertools.product((1, 3, 4), (0, 1), (1, 2)):
         taps = [(g.r, g.s) for _, _, gs in nhwc.plan_dgrad(ks, padding, stride) for g in gs]
         assert sorted(taps) == sorted(itertools.product(range(ks), range(ks)))
+
+
+def test_bench_tapconv_roofline_bookkeeping_on_the_emulation():
+    """bench.py's `roofline_tapconv` object: the launch it times is the one nhwc.conv plans (1 MMA term per tap for
+    single operands, 3 for 2-term split operands), and its FLOP accounting is 2*B*H*W*Cout*Cin*9 per launch."""
+    import bench
+    from oracle.nhwc_emul import EmulBackend
+    old = nhwc.set_backend(EmulBackend(exact=True))
+    try:
+        r = bench.tapconv_roofline(torch, batch=1, hw=8, cin=64, cout=64, iters=1, device="cpu")
+        assert "tapconv" not in vars(nhwc.backend())  # the capture hook is gone
+    finally:
+        nhwc.set_backend(old)
+    assert r["algorithmic_flops_per_launch"] == 2.0 * 8 * 8 * 64 * 64 * 9
+    assert r["single"]["mma_terms_per_tap"] == 1 and r["split3"]["mma_terms_per_tap"] == 3
+    for leg in ("single", "split3"):
+        assert r[leg]["executed"] == pytest.approx(r[leg]["mma_terms_per_tap"] * r[leg]["achieved"])
+        assert r[leg]["frac"] == pytest.approx(r[leg]["achieved"] / r["peak"])
