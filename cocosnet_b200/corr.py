@@ -239,7 +239,8 @@ def correspondence_tail(theta_conv, phi_conv, ref_img, *, match_kernel=3, pono_c
     if warp_mask_losstype == "cycle" and not want_direct:  # :337-346
         seg = F.interpolate(seg_map, scale_factor=1 / down, mode="nearest")
         to_ref = attend(phi, theta, seg.reshape(b, seg.shape[1], -1), scale, precision)
-        extras["warp_mask"] = attend(theta, phi, to_ref, scale, precision).reshape(b, -1, fh, fw)
+        # contiguous: F.nll_loss's backward rejects the permuted view the unfused (stock / CPU) expression returns
+        extras["warp_mask"] = attend(theta, phi, to_ref, scale, precision).reshape(b, -1, fh, fw).contiguous()
     if warp_cycle:  # :350-372
         if warp_patch:
             y_img = F.fold(y, 256, down, stride=down)

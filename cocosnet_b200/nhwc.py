@@ -330,6 +330,13 @@ def new(B, H, W, C, kind, device, pad=0, split=False, Cs=None, zero=None):
     return NT(t, kind, C, pad, lo)
 
 
+def _c4_gap(C):
+    """The norm / activation kernels write channels in groups of 4 (C rounded up to 4) while NT storage is padded to
+    8: when the two differ (C % 8 in 1..4) the last 4 slots are nobody's output and must be zero-filled up front --
+    they are read (times zero weights) by the convolution that consumes the tensor."""
+    return round_up(C, 4) != round_up(C, 8)
+
+
 def pack(src, kind=F16, pad=0, split=False, f=1, size=None):
     """fp32 NCHW -> NT (nearest down-sampling by the integer factor f to `size`, reflection halo, split)."""
     src = src.contiguous()
@@ -584,7 +591,7 @@ def bias_grad(dy):
 def act_bwd(dy, y, act, slope=0.0):
     """Gradient through a ReLU / LeakyReLU fused into a conv epilogue: dy bf16 and y share the halo; -> bf16, no halo."""
     assert dy.kind == BF16 and dy.pad == y.pad and act in (ACT_RELU, ACT_LRELU)
-    dz = new(y.B, y.H, y.W, y.C, BF16, y.t.device, zero=False)
+    dz = new(y.B, y.H, y.W, y.C, BF16, y.t.device, zero=_c4_gap(y.C))
     backend().act_bwd(dy, y, dz, round_up(y.C, 4), act, slope)
     return dz
 
@@ -625,8 +632,8 @@ def inst_act_fwd(x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, out_ki
     ([1,C4,2], batch_stats: BatchNorm2d); gb = [gamma | beta] NT: SPADE with those statistics (normalization.py:96-104).
     Returns (y NT, y2 NT | None): y2 = fp32 copy without halo (want_raw)."""
     assert x.pad == 0 and (gb is None or (gb.pad == 0 and gb.C == 2 * x.C and x.C % 4 == 0))
-    y = new(x.B, x.H, x.W, x.C, out_kind, x.t.device, pad=out_pad, split=split_out, zero=False)
-    y2 = new(x.B, x.H, x.W, x.C, F32, x.t.device, zero=False) if want_raw else None
+    y = new(x.B, x.H, x.W, x.C, out_kind, x.t.device, pad=out_pad, split=split_out, zero=_c4_gap(x.C))
+    y2 = new(x.B, x.H, x.W, x.C, F32, x.t.device, zero=_c4_gap(x.C)) if want_raw else None
     backend().inst_fwd(x, stats, res, slope_ptr, slope, y, y2, eps, round_up(x.C, 4), gb=gb, batch_stats=batch_stats)
     return y, y2
 
@@ -639,10 +646,10 @@ def inst_act_bwd(dy, x, stats, slope=1.0, slope_ptr=None, res=None, eps=1e-5, dy
     c4 = round_up(x.C, 4)
     dx_acc = dx is not None
     if dx is None:
-        dx = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=False)
+        dx = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=_c4_gap(x.C))
     dres_acc = dres is not None
     if want_dres and dres is None:
-        dres = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=False)
+        dres = new(x.B, x.H, x.W, x.C, BF16, x.t.device, zero=_c4_gap(x.C))
     dgb = new(x.B, x.H, x.W, 2 * x.C, BF16, x.t.device, zero=False) if gb is not None else None
     bstats = torch.empty((1 if batch_stats else x.B, c4, 2), dtype=torch.float32, device=x.t.device)
     args = (dy, dy2, x, stats, res, slope_ptr, slope, bstats, dslope, dx, dx_acc, dres if want_dres else None, dres_acc,

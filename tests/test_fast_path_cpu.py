@@ -111,3 +111,83 @@ def test_train_step_on_the_tape_matches_reference_golden(config):
             _, netk, pname = key.split("_", 2)
             p = dict(model.net[netk].named_parameters())[pname]
             assert abs(float(p.grad.norm()) - float(gold[key][0])) <= 2e-3 * float(gold[key][0]), key
+
+
+def _small_train_step(argv, fast, crop=64):
+    """One generator + discriminator pass at crop x crop through the tape on the emulation (fast) or through the plain
+    host mirror (COCOS_NHWC=0); returns (losses + outputs, gradients)."""
+    from cocosnet_b200.pix2pix_model import Pix2PixModel
+    saved = os.environ.get("COCOS_NHWC")
+    os.environ["COCOS_NHWC"] = "1" if fast else "0"
+    old = nhwc.set_backend(EmulBackend(exact=True))
+    try:
+        opt = TrainOptions().parse(argv + ["--batchSize", "1", "--gpu_ids", "-1", "--crop_size", str(crop), "--load_size",
+                                           str(crop)], save=False, verbose=False)
+        opt.verbose_networks = False
+        opt.allow_random_vgg = True
+        torch.manual_seed(0)
+        model = Pix2PixModel(opt)
+        model.vggnet_fix.load_state_dict(torch_port.seeded_vgg_state_dict())
+        model.train()
+        batch = cdata.synthetic_batch(opt, 1)
+        with torch_port.cpu_reference_mode():
+            g_losses, out = model(batch, mode="generator")
+            sum(g_losses.values()).mean().backward()
+            grads = {k + "/" + n: p.grad.clone() for k in ("netG", "netCorr")
+                     for n, p in model.net[k].named_parameters() if p.grad is not None}
+            d_losses = model(batch, mode="discriminator", GforD={"fake_image": out["fake_image"]})
+            sum(d_losses.values()).mean().backward()
+            grads.update({"netD/" + n: p.grad.clone() for n, p in model.net["netD"].named_parameters()
+                          if p.grad is not None})
+    finally:
+        nhwc.set_backend(old)
+        if saved is None:
+            os.environ.pop("COCOS_NHWC")
+        else:
+            os.environ["COCOS_NHWC"] = saved
+    vals = {"g_" + k: v.detach().reshape(-1) for k, v in g_losses.items()}
+    vals.update({"d_" + k: v.detach().reshape(-1) for k, v in d_losses.items()})
+    vals.update(fake_image=out["fake_image"].detach(), warp_out=out["warp_out"].detach())
+    return vals, grads
+
+
+SMALL = {
+    # 256 + 151 + 2 = 409 channels in the residual stack: C % 8 == 1 (unwritten channel slots, see
+    # test_norm_act_outputs_leave_no_uninitialised_channel_slots)
+    "coordconv_409": ["--dataset_mode", "ade20k", "--PONO", "--PONO_C", "--maskmix", "--use_coordconv"],
+    # 256 + 19 = 275 channels, batch-statistics SPADE, bilinear warp, cycle term, attention
+    "celebahq_maskmix_275": ["--dataset_mode", "celebahq", "--maskmix", "--use_attention", "--warp_bilinear",
+                             "--warp_cycle_w", "0.1"],
+    # column-softmax mask (correspondence.py:337-346)
+    "cycle_mask": ["--dataset_mode", "ade20k", "--PONO", "--PONO_C", "--maskmix", "--warp_mask_losstype", "cycle"],
+    # 4x4 adaptor kernels + edge maps as labels + the two-cycle term
+    "celebahqedge_two_cycle": ["--dataset_mode", "celebahqedge", "--PONO", "--PONO_C", "--adaptor_kernel", "4",
+                               "--warp_cycle_w", "1.0", "--two_cycle"],
+}
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name", list(SMALL))
+def test_tape_equals_plain_mirror_on_other_flag_sets(name):
+    """Flag sets without a reference golden, at 64x64 so that they are cheap: the tape (every network on the kernel
+    emulation) against the plain host mirror, which test_model_parity_cpu.py pins to the reference.  Losses and outputs
+    to fp32 rounding; gradients to 1e-2 (1/T = 100 amplifies rounding into the correspondence gradients), skipping
+    parameters whose gradient is analytically zero (biases in front of a normalisation)."""
+    want, gw = _small_train_step(SMALL[name], fast=False)
+    got, gg = _small_train_step(SMALL[name], fast=True)
+    assert set(want) == set(got) and set(gw) == set(gg)
+    for k in want:
+        d = float((want[k].double() - got[k].double()).norm() / (want[k].double().norm() + 1e-30))
+        assert d < 1e-4, (k, d)
+    med = {}
+    for k, v in gw.items():
+        med.setdefault(k.split("/")[0], []).append(float(v.norm()))
+    med = {k: float(np.median(v)) for k, v in med.items()}
+    checked = 0
+    for k, v in gw.items():
+        if float(v.norm()) < 1e-2 * med[k.split("/")[0]]:
+            continue
+        d = float((v.double() - gg[k].double()).norm() / v.double().norm())
+        assert d < 1e-2, (k, d)
+        checked += 1
+    assert checked > 100

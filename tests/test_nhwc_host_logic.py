@@ -196,3 +196,32 @@ def test_bench_tapconv_roofline_bookkeeping_on_the_emulation():
     for leg in ("single", "split3"):
         assert r[leg]["executed"] == pytest.approx(r[leg]["mma_terms_per_tap"] * r[leg]["achieved"])
         assert r[leg]["frac"] == pytest.approx(r[leg]["achieved"] / r["peak"])
+
+
+@pytest.mark.parametrize("C", [409, 275, 66, 407, 64])
+def test_norm_act_outputs_leave_no_uninitialised_channel_slots(C):
+    """The norm / activation kernels write channels in groups of 4, NT storage is padded to 8: for C % 8 in 1..4 (the
+    residual stack with --use_coordconv: 409 channels; celebahq + --maskmix: 275) the last four slots belong to nobody
+    and have to be zero-filled by the allocation -- the next convolution reads them (times zero weights).  The emulation
+    NaN-poisons unwritten memory, so a consumer of such a slot trips its assertion."""
+    old = nhwc.set_backend(EmulBackend(exact=True))
+    try:
+        g = torch.Generator().manual_seed(C)
+        x = torch.randn(2, C, 8, 8, generator=g)
+        w = torch.randn(C, C, 3, 3, generator=g) * 0.02
+        r = nhwc.conv(nhwc.pack(x, nhwc.F16, pad=1, split=True), w, None, out_kind=nhwc.F32)
+        stats = nhwc.in_stats(r)
+        a = torch.tensor([0.25])
+        y, y2 = nhwc.inst_act_fwd(r, stats, slope_ptr=a, out_kind=nhwc.F16, out_pad=1, split_out=True, want_raw=True)
+        assert torch.isfinite(y.t.float()).all() and torch.isfinite(y2.t).all()
+        nhwc.conv(y, w, None, out_kind=nhwc.F32)  # asserts on a non-finite operand
+        dy = nhwc.new(2, 8, 8, C, nhwc.BF16, x.device, pad=1)
+        dy.t.normal_(generator=g)
+        dy.t[..., C:] = 0
+        dslope = torch.zeros(1)
+        dx, dres, _ = nhwc.inst_act_bwd(dy, r, stats, slope_ptr=a, res=y2, want_dres=True, dslope=dslope)
+        assert torch.isfinite(dx.t.float()).all() and torch.isfinite(dres.t.float()).all()
+        dz = nhwc.act_bwd(dy, y, nhwc.ACT_LRELU, 0.2)
+        assert torch.isfinite(dz.t.float()).all()
+    finally:
+        nhwc.set_backend(old)
