@@ -407,6 +407,8 @@ def discriminator_supported(net, sem, img):
         if layers is None or (D.use_attn and not any(n == "model3" for n, _, _, _ in layers)):
             return False
         hh, ww = h, w
+        if any(conv.out_channels % 8 for _, conv, _, _ in layers[:-1]):
+            return False  # feature widths off the 8-channel storage grid (--ndf not a multiple of 8): the module path
         for _, conv, _, _ in layers:
             if conv.stride == (2, 2) and (hh % 2 or ww % 2):
                 return False  # the stride-2 parity view needs even input sizes
