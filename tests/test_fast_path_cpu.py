@@ -151,43 +151,39 @@ def _small_train_step(argv, fast, crop=64):
     return vals, grads
 
 
-SMALL = {
-    # 256 + 151 + 2 = 409 channels in the residual stack: C % 8 == 1 (unwritten channel slots, see
-    # test_norm_act_outputs_leave_no_uninitialised_channel_slots)
-    "coordconv_409": ["--dataset_mode", "ade20k", "--PONO", "--PONO_C", "--maskmix", "--use_coordconv"],
-    # 256 + 19 = 275 channels, batch-statistics SPADE, bilinear warp, cycle term, attention
-    "celebahq_maskmix_275": ["--dataset_mode", "celebahq", "--maskmix", "--use_attention", "--warp_bilinear",
-                             "--warp_cycle_w", "0.1"],
-    # column-softmax mask (correspondence.py:337-346)
-    "cycle_mask": ["--dataset_mode", "ade20k", "--PONO", "--PONO_C", "--maskmix", "--warp_mask_losstype", "cycle"],
-    # 4x4 adaptor kernels + edge maps as labels + the two-cycle term
-    "celebahqedge_two_cycle": ["--dataset_mode", "celebahqedge", "--PONO", "--PONO_C", "--adaptor_kernel", "4",
-                               "--warp_cycle_w", "1.0", "--two_cycle"],
-}
+from tests.golden.cases_small import SMALL_CASES  # noqa: E402
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("name", list(SMALL))
-def test_tape_equals_plain_mirror_on_other_flag_sets(name):
-    """Flag sets without a reference golden, at 64x64 so that they are cheap: the tape (every network on the kernel
-    emulation) against the plain host mirror, which test_model_parity_cpu.py pins to the reference.  Losses and outputs
-    to fp32 rounding; gradients to 1e-2 (1/T = 100 amplifies rounding into the correspondence gradients), skipping
-    parameters whose gradient is analytically zero (biases in front of a normalisation)."""
-    want, gw = _small_train_step(SMALL[name], fast=False)
-    got, gg = _small_train_step(SMALL[name], fast=True)
-    assert set(want) == set(got) and set(gw) == set(gg)
-    for k in want:
-        d = float((want[k].double() - got[k].double()).norm() / (want[k].double().norm() + 1e-30))
-        assert d < 1e-4, (k, d)
-    med = {}
-    for k, v in gw.items():
-        med.setdefault(k.split("/")[0], []).append(float(v.norm()))
-    med = {k: float(np.median(v)) for k, v in med.items()}
+@pytest.mark.parametrize("name", list(SMALL_CASES))
+def test_small_flag_sets_match_reference_golden(name):
+    """17 more flag sets at 64x64 against goldens minted from the UNMODIFIED reference (tests/golden/
+    make_golden_small.py): the option branches the three 256x256 goldens do not reach -- odd channel counts in the
+    residual stack (--use_coordconv 409, celebahq / deepfashion + --maskmix 275 / 276: C % 8 in 1..4 needs zero-filled
+    channel slots), the column-softmax mask, both cycle terms, the other GAN modes, adaptor variants, D_cam ...  Run with
+    the tape on the kernel emulation: whatever the tape supports runs on it, the rest on the mirror modules -- exactly
+    the dispatch a GPU run does.  Losses / outputs to fp32 rounding; gradient norms to 2e-2: 1/T = 100 amplifies fp32
+    rounding into the correspondence gradients, and at this size the REFERENCE's own fp32 gradients are the noisy side --
+    against an fp64 evaluation of the same step (match_kernel_1) the reference / mirror arithmetic is off by 1.2e-2 on
+    the PReLU slopes and 1e-3 on theta / phi, the tape by 3e-4 / 1e-5 (its convolutions accumulate in a different order)."""
+    gold = np.load(os.path.join(GOLD, "small_%s.npz" % name))
+    got, grads = _small_train_step(SMALL_CASES[name], fast=True)
+    for key in gold.files:
+        if key.startswith(("g_", "d_")):
+            assert np.allclose(got[key].numpy(), gold[key], rtol=5e-4, atol=2e-6), (key, got[key], gold[key])
+    assert {k for k in got if k.startswith(("g_", "d_"))} == {k for k in gold.files if k.startswith(("g_", "d_"))}
+    assert np.allclose(got["fake_image"].numpy()[:, :, ::2, ::2], gold["fake_image_sub"], atol=5e-5)
+    assert np.allclose(got["warp_out"].numpy()[:, :, ::2, ::2], gold["warp_out_sub"], atol=5e-5)
     checked = 0
-    for k, v in gw.items():
-        if float(v.norm()) < 1e-2 * med[k.split("/")[0]]:
-            continue
-        d = float((v.double() - gg[k].double()).norm() / v.double().norm())
-        assert d < 1e-2, (k, d)
-        checked += 1
-    assert checked > 100
+    for key in gold.files:
+        if key.startswith("gradnorm_"):
+            _, netk, pname = key.split("_", 2)
+            want = float(gold[key][0])
+            g = grads[netk + "/" + pname]
+            have = float(g.norm())
+            # scalar parameters (PReLU slopes, attn.gamma) are one big cancelling sum: the reference's fp32 value is
+            # up to 3e-2 from the fp64 one (cbn_mask: attn.gamma 0.06351 vs 0.06171 in fp64; the tape gives 0.06170)
+            tol = 5e-2 if g.numel() <= 16 else 2e-2
+            assert abs(have - want) <= tol * want + 1e-7, (key, have, want)
+            checked += 1
+    assert checked >= 10
