@@ -301,6 +301,11 @@ def inst_act(tp, x, slope=1.0, prelu=None, res=None, eps=1e-5, out_kind=F16, out
     return out, out2
 
 
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def _avg_over_ranks(t):
     """In-place mean over the data-parallel ranks (SynchronizedBatchNorm2d semantics: statistics of the global batch)."""
     import torch.distributed as dist
@@ -334,7 +339,8 @@ def spade_stat(tp, x, gb, pnorm, pad, slope, split):
                 var = (stats[0, :C, 1] / n - mean * mean).clamp_min_(0)
                 mom = pnorm.momentum if pnorm.momentum is not None else 0.1
                 pnorm.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-                pnorm.running_var.mul_(1 - mom).add_(var * (n / max(n - 1, 1)), alpha=mom)
+                ng = n * _world()  # the unbiased estimate counts the GLOBAL batch (SynchronizedBatchNorm2d)
+                pnorm.running_var.mul_(1 - mom).add_(var * (ng / max(ng - 1, 1)), alpha=mom)
                 if pnorm.num_batches_tracked is not None:
                     pnorm.num_batches_tracked += 1
     else:  # eval: the running estimates, in the (sum, sum of squares) form the kernels take

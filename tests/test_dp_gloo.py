@@ -75,3 +75,84 @@ def test_shard_batch_is_contiguous():
     assert torch.equal(s1["image"], d["image"][4:]) and s1["path"] == d["path"][4:]
     with pytest.raises(AssertionError):
         tr.shard_batch(d, rank=0, world=3)
+
+
+# ---- batch-statistics SPADE across ranks (the reference's SynchronizedBatchNorm2d, normalization.py:96-104) ----
+SYNCBN_ARGV = ["--dataset_mode", "celebahq", "--warp_bilinear", "--adaptor_kernel", "4", "--gpu_ids", "-1",
+               "--crop_size", "64", "--load_size", "64", "--batchSize", "2"]
+
+
+def _celebahq_grads(shard=None):
+    """One generator pass + backward of the celebahq model (SPADE with batch statistics, no --PONO) at 64x64 with the
+    tape on the kernel emulation; shard = (rank, world): this rank's slice of the 2-image batch, gradients averaged
+    over the ranks as the trainer does.  Returns (losses, gradients, BatchNorm running estimates)."""
+    from cocosnet_b200 import data as cdata
+    from cocosnet_b200 import nhwc
+    from cocosnet_b200 import trainer as tr
+    from cocosnet_b200.options import TrainOptions
+    from cocosnet_b200.pix2pix_model import Pix2PixModel
+    from oracle import torch_port
+    from oracle.nhwc_emul import EmulBackend
+    old = nhwc.set_backend(EmulBackend(exact=True))
+    try:
+        opt = TrainOptions().parse(SYNCBN_ARGV, save=False, verbose=False)
+        opt.verbose_networks = False
+        opt.allow_random_vgg = True
+        torch.manual_seed(0)
+        model = Pix2PixModel(opt)
+        model.vggnet_fix.load_state_dict(cdata.seeded_vgg_state_dict())
+        model.train()
+        batch = cdata.synthetic_batch(opt, 2)
+        if shard is not None:
+            batch = tr.shard_batch(batch, rank=shard[0], world=shard[1])
+        with torch_port.cpu_reference_mode():
+            g_losses, _ = model(batch, mode="generator")
+            sum(g_losses.values()).mean().backward()
+        params = [p for k in ("netG", "netCorr") for p in model.net[k].parameters() if p.grad is not None]
+        if shard is not None:
+            tr.allreduce_grads(params)
+        grads = {k + "/" + n: p.grad.clone() for k in ("netG", "netCorr") for n, p in model.net[k].named_parameters()
+                 if p.grad is not None}
+        stats = {k + "/" + n: b.clone() for k in ("netG", "netCorr") for n, b in model.net[k].named_buffers()
+                 if n.endswith(("running_mean", "running_var"))}
+        return {k: float(v.detach().mean()) for k, v in g_losses.items()}, grads, stats
+    finally:
+        nhwc.set_backend(old)
+
+
+def _syncbn_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.save(_celebahq_grads((rank, world)), os.path.join(out_dir, "syncbn%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_batch_statistics_spade_is_synchronised_over_ranks(tmp_path):
+    """Two ranks with one image each == one process with both images: the SPADE layers' batch statistics (forward) and
+    the two reductions of their backward are averaged over the ranks inside the tape (tape.spade_stat), so losses,
+    averaged gradients and the running estimates agree with the global-batch computation.  Unsynchronised statistics
+    (one image instead of two) would move all three by tens of percent."""
+    port = _free_port()
+    mp.spawn(_syncbn_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (l0, g0, s0), (l1, g1, s1) = (torch.load(os.path.join(tmp_path, "syncbn%d.pt" % r)) for r in (0, 1))
+    lw, gw, sw = _celebahq_grads()
+    assert len(sw) > 40
+    for k in sw:  # same estimates on both ranks, equal to the global-batch ones
+        assert torch.equal(s0[k], s1[k]), k
+        assert torch.allclose(s0[k], sw[k], rtol=1e-4, atol=1e-6), (k, float((s0[k] - sw[k]).abs().max()))
+    for k in lw:
+        assert abs(0.5 * (l0[k] + l1[k]) - lw[k]) <= 2e-4 * abs(lw[k]) + 1e-6, (k, l0[k], l1[k], lw[k])
+    med = sorted(float(v.norm()) for v in gw.values())[len(gw) // 2]
+    checked = 0
+    for k, v in gw.items():
+        assert torch.equal(g0[k], g1[k]), k
+        if float(v.norm()) < 1e-2 * med:
+            continue  # analytically zero (a bias in front of a normalisation): rounding noise
+        d = float((g0[k] - v).norm() / v.norm())
+        assert d < 2e-2, (k, d)
+        checked += 1
+    assert checked > 150
