@@ -156,3 +156,81 @@ def test_batch_statistics_spade_is_synchronised_over_ranks(tmp_path):
         assert d < 2e-2, (k, d)
         checked += 1
     assert checked > 150
+
+
+# ---- the whole trainer iteration at world size 2 (the tape on the kernel emulation) ----
+TRAINER_ARGV = ["--dataset_mode", "ade20k", "--PONO", "--PONO_C", "--use_attention", "--maskmix", "--gpu_ids", "-1",
+                "--crop_size", "64", "--load_size", "64", "--batchSize", "2"]
+
+
+def _trainer_grads():
+    """run_generator_one_step + run_discriminator_one_step of the real trainer (shard, backward, all-reduce) with the
+    optimiser steps replaced by recorders: the gradients each optimiser would have consumed."""
+    from cocosnet_b200 import data as cdata
+    from cocosnet_b200 import nhwc
+    from cocosnet_b200.options import TrainOptions
+    from cocosnet_b200.trainer import Pix2PixTrainer
+    from oracle import torch_port
+    from oracle.nhwc_emul import EmulBackend
+    old = nhwc.set_backend(EmulBackend(exact=True))
+    try:
+        opt = TrainOptions().parse(TRAINER_ARGV, save=False, verbose=False)
+        opt.verbose_networks = False
+        opt.allow_random_vgg = True
+        torch.manual_seed(0)
+        trainer = Pix2PixTrainer(opt)
+        model = trainer.pix2pix_model
+        model.vggnet_fix.load_state_dict(cdata.seeded_vgg_state_dict())
+        seen = {}
+
+        def recorder(nets):
+            def step():
+                for k in nets:
+                    for n, p in model.net[k].named_parameters():
+                        if p.grad is not None:
+                            seen[k + "/" + n] = p.grad.clone()
+            return step
+        trainer.optimizer_G.step = recorder(("netG", "netCorr"))
+        trainer.optimizer_D.step = recorder(("netD",))
+        batch = cdata.synthetic_batch(opt, 2)  # the GLOBAL batch on every rank: the trainer takes this rank's slice
+        with torch_port.cpu_reference_mode():
+            trainer.run_generator_one_step(batch)
+            trainer.run_discriminator_one_step(batch)
+        losses = {k: float(v.detach().mean()) for k, v in trainer.get_latest_losses().items()}
+        return losses, seen
+    finally:
+        nhwc.set_backend(old)
+
+
+def _trainer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.save(_trainer_grads(), os.path.join(out_dir, "trainer%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_trainer_iteration_on_two_ranks_matches_the_global_batch(tmp_path):
+    """The reference's nn.DataParallel step (pix2pix_trainer.py:23-26,52-74) as one process per GPU: each rank runs the
+    G and D steps on its contiguous half of the batch and averages the gradients.  Every loss term of this flag set is a
+    mean over samples, so the averaged gradients equal those of one process on the whole batch."""
+    port = _free_port()
+    mp.spawn(_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (l0, g0), (l1, g1) = (torch.load(os.path.join(tmp_path, "trainer%d.pt" % r)) for r in (0, 1))
+    lw, gw = _trainer_grads()
+    assert set(g0) == set(gw) and len(gw) > 300
+    for k in lw:
+        assert abs(0.5 * (l0[k] + l1[k]) - lw[k]) <= 2e-4 * abs(lw[k]) + 1e-6, (k, l0[k], l1[k], lw[k])
+    med = sorted(float(v.norm()) for v in gw.values())[len(gw) // 2]
+    checked = 0
+    for k, v in gw.items():
+        assert torch.equal(g0[k], g1[k]), k
+        if float(v.norm()) < 1e-2 * med:
+            continue
+        d = float((g0[k] - v).norm() / v.norm())
+        assert d < 2e-2, (k, d)
+        checked += 1
+    assert checked > 250
