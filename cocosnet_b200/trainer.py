@@ -141,15 +141,8 @@ class Pix2PixTrainer:
                 and os.environ.get("COCOS_CUDA_GRAPH", "1") == "1" and self.graph_error is None)
 
     def _eager_step(self, data, alpha=1):
-        # EXPERIMENTAL (COCOS_DEFER_G_STEP=1, off by default): keep the generator's gradient all-reduces running on
-        # NCCL's stream underneath the whole discriminator step (which reads neither netG nor netCorr parameters) and
-        # defer optimizer_G.step() until after it.  Measured 0.987 at N = 2, but the N = 8 run did not finish within its
-        # time limit (profiles/r02_scale_README.txt), so the validated schedule stays the default: netG's all-reduce
-        # under netCorr's backward, the rest and the optimiser step right after the backward.
-        finish = self.run_generator_one_step(data, alpha, defer_step=os.environ.get("COCOS_DEFER_G_STEP", "0") == "1")
+        self.run_generator_one_step(data, alpha)
         self.run_discriminator_one_step(data)
-        if finish is not None:
-            finish()
 
     def _load_static(self, data):
         for k, buf in self._static_in.items():
@@ -258,9 +251,7 @@ class Pix2PixTrainer:
         (a per-rank data loader, bench.py's weak-scaling batches)."""
         return data if self.pre_sharded else shard_batch(data)
 
-    def run_generator_one_step(self, data, alpha=1, defer_step=False):
-        """defer_step (only honoured with NCCL ranks): return a callable that waits for the gradient all-reduces and
-        applies optimizer_G.step() (+ EMA) instead of doing so here."""
+    def run_generator_one_step(self, data, alpha=1):
         self.optimizer_G.zero_grad(set_to_none=True)
         # The G step only needs the gradient THROUGH the discriminator, not its weight gradients (the reference
         # computes and then discards them: optimizer_D.zero_grad() runs before they are ever used).
@@ -291,23 +282,18 @@ class Pix2PixTrainer:
                 p.requires_grad_(True)
         self.g_losses, self.out = g_losses, out
         if overlap and pending:
-            pending.append(allreduce_grads([p for p in self.pix2pix_model.net["netCorr"].parameters()], async_op=defer_step))
+            allreduce_grads([p for p in self.pix2pix_model.net["netCorr"].parameters()])
         else:
             allreduce_grads(self._g_params)
             pending = []
 
-        def finish():
-            for h in pending:
-                if h is not None:
-                    h.wait()
-            self.optimizer_G.step()
-            if self.opt.use_ema:
-                self.netG_ema(self.pix2pix_model.net["netG"])
-                self.netCorr_ema(self.pix2pix_model.net["netCorr"])
-        if defer_step and overlap and pending:
-            return finish
-        finish()
-        return None
+        for h in pending:  # netG's early all-reduce
+            if h is not None:
+                h.wait()
+        self.optimizer_G.step()
+        if self.opt.use_ema:
+            self.netG_ema(self.pix2pix_model.net["netG"])
+            self.netCorr_ema(self.pix2pix_model.net["netCorr"])
 
     def run_discriminator_one_step(self, data):
         self.optimizer_D.zero_grad(set_to_none=True)
