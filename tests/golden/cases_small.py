@@ -33,3 +33,8 @@ SMALL_CASES = {
     # instance statistics in SPADE (at batch 1 the same numbers as the default batch statistics: another kernel path)
     "no_pono_instance_stats": ["--dataset_mode", "ade20k", "--norm_G", "spectralspadeinstance3x3"],
 }
+
+# the module-only variants (the tape does not take these layers: they pin the mirror modules, not the kernels' host
+# side) run when COCOS_ALL_SMALL_CASES=1; the default CPU suite keeps to the cases that reach the tape
+EXTENDED_ONLY = ("original_gan_fm_ratio", "adaptor_se_deeper", "adaptor_nonlocal_dilation", "eqlr_sn", "d_cam",
+                 "domain_classifier")
